@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""Benchmark of the Noah-MP column time step on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle restatement)
+
+metric   cell-timesteps/s  = columns x model-steps advanced per second, whole job (all ranks)
+step     one launch of the step kernel advancing EVERY column of the workload by the workload's
+         `model_steps` time steps (time-fused in one kernel; forcing of every model step is read from HBM)
+workload BASELINE.json configs[3]: CONUS 1 km synthetic grid, 17e6 columns x 24 hourly steps, mixed
+         soil/vegetation types, block-partitioned over the ranks (strong scaling, no data-path collective;
+         one NCCL all-reduce of the 16 budget sums after the timed region)
+value    inputs resident in HBM; CUDA events on the launching stream; max over ranks
+e2e      the same work through the C-ABI host entry point `noahmp_run_host` with pinned HOST buffers:
+         H2D of state+forcing+static and D2H of state inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from noahmp_b200 import layout as L, synth  # noqa: E402
+from noahmp_b200.tables import ParamTables  # noqa: E402
+
+B_ALG = 404  # algorithmic bytes per cell-step (SURVEY 8d / DESIGN.md section 4)
+METRIC = "cell_timesteps_per_sec"
+UNIT = "cell-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="conus1km")
+    ap.add_argument("--ncol", type=int, default=None, help="override the workload's TOTAL column count")
+    ap.add_argument("--model-steps", type=int, default=None, help="override model time steps per launch")
+    ap.add_argument("--variant", default="parity", choices=["parity", "fast", "strict"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-cols", type=int, default=1_000_000)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def shard(ncol: int, rank: int, world: int):
+    per = (ncol + world - 1) // world
+    c0 = min(rank * per, ncol)
+    return c0, min(c0 + per, ncol) - c0
+
+
+def build_workload(args):
+    w = synth.make_workload(args.workload, ncol=args.ncol, nsteps=args.model_steps)
+    return w
+
+
+def slice_workload(w, c0, n):
+    import copy
+    s = copy.copy(w)
+    s.ncol = n
+    s.state = np.ascontiguousarray(w.state[:, c0:c0 + n])
+    s.static_f = np.ascontiguousarray(w.static_f[:, c0:c0 + n])
+    s.static_i = np.ascontiguousarray(w.static_i[c0:c0 + n])
+    s.sincos = np.ascontiguousarray(w.sincos[:, c0:c0 + n])
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(w, sample_cols: int, fast: bool = True, repeats: int = 1) -> dict:
+    """The reference's CPU path (C++ restatement of core/module_noahmp_func.f90; the Fortran cannot be
+    compiled here) on all host cores, on the first `sample_cols` columns x all model steps."""
+    from oracle.oracle import Oracle
+    n = min(sample_cols, w.ncol)
+    ws = slice_workload(w, 0, n)
+    forcing = synth.forcing_all(ws, col0=0)
+    o = Oracle(ParamTables.default(), w.opts, fast="fast" if fast else "parity")
+    best = None
+    for _ in range(repeats):
+        st = ws.state.copy()
+        t0 = time.perf_counter()
+        o.run_workload(ws, forcing, state=st)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": n * w.nsteps / best, "unit": UNIT, "cores": o.num_threads(), "kind": "port",
+            "sample": f"first {n} columns x {w.nsteps} model steps of {w.name} ({'-O3 AVX2+FMA' if fast else '-O2 no-FMA'} build, "
+                      f"OpenMP static, {best:.2f} s)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = build_workload(args)
+    n = min(args.cpu_sample_cols, w.ncol)
+    from oracle.oracle import Oracle
+    ws = slice_workload(w, 0, n)
+    forcing = synth.forcing_all(ws, col0=0)
+    o = Oracle(ParamTables.default(), w.opts, fast="fast")
+    times = []
+    for it in range(args.warmup + args.steps):
+        st = ws.state.copy()
+        t0 = time.perf_counter()
+        o.run_workload(ws, forcing, state=st)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = n * w.nsteps * len(times) / total
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "columns": w.ncol, "model_steps_per_step": w.nsteps, "dt_s": w.dt,
+                       "options": w.opts, "sampled_columns": n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": o.num_threads(), "kind": "port",
+                             "sample": f"first {n} columns x {w.nsteps} model steps per step (-O3 AVX2+FMA build of the C++ "
+                                       "restatement; the reference Fortran cannot be compiled in this image)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from noahmp_b200.engine import NoahMP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA GPU (no CPU fallback exists)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = build_workload(args)
+    c0, nloc = shard(w.ncol, rank, world)
+    ws = slice_workload(w, c0, nloc)
+    eng = NoahMP(ParamTables.default(), w.opts, device=local, fast=args.variant)
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream)
+    rp_of = lambda j0: eng.run_params(w.dt, synth.ZSOIL, j0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)  # noqa: E731
+
+    # ---- inputs resident in HBM: state, static, forcing of every model step (generated on device) -----
+    launches0 = eng.launch_count()
+    with torch.cuda.stream(stream):
+        state0 = torch.from_numpy(ws.state).to(dev)
+        state = state0.clone()
+        static_f = torch.from_numpy(ws.static_f).to(dev)
+        static_i = torch.from_numpy(ws.static_i).to(dev)
+        sincos = torch.from_numpy(ws.sincos).to(dev)
+        forcing = torch.empty((w.nsteps, L.NFORCING, nloc), dtype=torch.float32, device=dev)
+        coef = synth.synth_params_array(w.synth)
+        for s in range(w.nsteps):
+            sc = synth.step_scalars(w, s)
+            eng.synth_forcing(nloc, c0, w.synth.seed, s, coef,
+                              np.asarray([sc["sd"], sc["cdch"], sc["t_diur"], sc["t_seas"]], np.float32), sincos, forcing[s])
+        budget = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
+    stream.synchronize()
+
+    def one_step(k):
+        # the simulation simply continues: bench step k starts model time at julian0 + k*model_steps*dt
+        eng.run(rp_of(w.julian0 + k * w.nsteps * w.dt / 86400.0), state, forcing, static_f, static_i)
+
+    with torch.cuda.stream(stream):
+        for k in range(args.warmup):
+            one_step(k)
+    stream.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = eng.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        evs[0].record(stream)
+        for k in range(args.steps):
+            one_step(args.warmup + k)
+            evs[k + 1].record(stream)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    t_max = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t_max.item())
+
+    # ---- budget diagnostics of one extra pass + the only collective of the path (outside the timed region)
+    with torch.cuda.stream(stream):
+        chk = state0.clone()
+        eng.run(rp_of(w.julian0), chk, forcing, static_f, static_i, None, budget)
+    stream.synchronize()
+    bsum = budget.clone()
+    bmax = budget[L.B["ERRWAT_MAXABS"]].clone()
+    if world > 1:
+        bsum[L.B["ERRWAT_MAXABS"]] = 0.0
+        dist.all_reduce(bsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
+    bsum[L.B["ERRWAT_MAXABS"]] = bmax
+    bud = {L.BUDGET[i]: float(bsum[i].item()) for i in range(L.NBUDGET)}
+
+    # ---- e2e: host buffers through noahmp_run_host --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nplanes = L.NSTATE_CORE if w.opts == synth.DEFAULT_OPTS else L.NSTATE
+        h_state = torch.from_numpy(ws.state.copy()).pin_memory()
+        h_forcing = torch.empty((w.nsteps, L.NFORCING, nloc), dtype=torch.float32).pin_memory()
+        h_forcing.copy_(forcing)
+        h_sf = torch.from_numpy(ws.static_f).pin_memory()
+        h_si = torch.from_numpy(ws.static_i).pin_memory()
+        torch.cuda.synchronize()
+        ne2e = max(1, min(args.steps, 3))
+        eng.run_host(rp_of(w.julian0), h_state, h_forcing, h_sf, h_si)       # warm-up (allocates device staging)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(ne2e):
+            eng.run_host(rp_of(w.julian0 + (k + 1) * w.nsteps * w.dt / 86400.0), h_state, h_forcing, h_sf, h_si)
+        dt_e = time.perf_counter() - t0
+        t_e = torch.tensor([dt_e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        h2d = 4 * nloc * (nplanes + w.nsteps * L.NFORCING + L.NSTATIC_F + 1)
+        d2h = 4 * nloc * nplanes
+        e2e = {"value": w.ncol * w.nsteps * ne2e / float(t_e.item()), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "steps": ne2e, "flagged_columns": None}
+        del h_state, h_forcing
+
+    if rank == 0:
+        value = w.ncol * w.nsteps * args.steps / (total_ms_max * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        k_ms = float(np.mean(per_launch_ms))
+        achieved = B_ALG * nloc * w.nsteps / (k_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w.name, "columns": w.ncol, "columns_per_gpu": nloc, "model_steps_per_step": w.nsteps,
+                           "dt_s": w.dt, "options": w.opts, "variant": args.variant, "partition": f"block x{world}",
+                           "l2": "inputs larger than L2 (state+forcing per launch >> 126 MB); no flush needed"
+                                 if nloc * 4 * (2 * 44 + 9 * w.nsteps) > 2 * 126e6 else "inputs fit L2: traffic is L2-resident",
+                           "kernel": eng.kernel_info()},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "bytes_per_cell_step": B_ALG,
+                             "kernel": "column_step_kernel", "kernel_ms": k_ms,
+                             "note": "kernel is instruction-issue bound (see profiles/); fraction is reported against HBM as "
+                                     "the contract asks"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "budget": bud}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(w, args.cpu_sample_cols)
+        elif not args.no_cpu_baseline:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+/* noahmp_b200 -- C ABI of the B200-native Noah-MP column time step.
+ *
+ * This library fills the slot the reference leaves empty: core/module_noahmp_engine.f90:5-10 declares
+ * `noahmp_init` and `noahmp_run` with no arguments and no body, and nothing in the reference ever calls
+ * the one-column physics routine `noahmp_sflx` (core/module_noahmp_func.f90:66-91).  Here `noahmp_run`
+ * advances ALL columns of a structure-of-arrays batch on one GPU; per column the semantics are those of
+ * one `noahmp_sflx` call per step.  Plain C types only; all pointers named *_dev are CUDA device
+ * pointers owned by the caller (e.g. torch tensors' data_ptr()), all others are host pointers.
+ *
+ * Return convention (replaces the reference's `stop` in utils:43-53 / wrf_error_fatal sites):
+ *   0 = OK, < 0 = API misuse or CUDA error (text via noahmp_last_error), > 0 = number of columns whose
+ *   error-flag word is non-zero (only reported by calls that compute it).  Nothing aborts or throws.
+ */
+#ifndef NOAHMP_B200_H
+#define NOAHMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct noahmp_ctx noahmp_ctx;
+
+/* ---- plane counts (see noahmp_layout) -------------------------------------------------------- */
+#define NOAHMP_NSTATE      57  /* 44 core planes + 13 extended (SURVEY App. A groups S and s)      */
+#define NOAHMP_NSTATE_CORE 44
+#define NOAHMP_NFORCING     9  /* SFCTMP SFCPRS UU VV Q2 SOLDN LWDN PRCP COSZ  (func:72-74)        */
+#define NOAHMP_NSTATIC_F    4  /* LAT SHDFAC TBOT SHDMAX                                           */
+#define NOAHMP_NDIAG       63  /* 58 outputs of func:82-91 + ERRWAT ERRSW ERRENG ITER FLAGS        */
+#define NOAHMP_NBUDGET     16
+#define NOAHMP_NGEN        53
+#define NOAHMP_NSOILP      10
+#define NOAHMP_NCOLORP      4
+#define NOAHMP_NVEGF       71
+#define NOAHMP_NVEGI        2
+
+/* error-flag bits: one per fatal site of the reference */
+#define NOAHMP_FLAG_ERRSW   (1u << 0) /* func:688-710  */
+#define NOAHMP_FLAG_ERRENG  (1u << 1) /* func:712-721  */
+#define NOAHMP_FLAG_FIRE    (1u << 2) /* func:1286-1292 */
+#define NOAHMP_FLAG_HCAN    (1u << 3) /* func:2726-2738 */
+#define NOAHMP_FLAG_ZLVL    (1u << 4) /* func:3412-3415 */
+#define NOAHMP_FLAG_OPTVEG  (1u << 5) /* func:375-378  */
+#define NOAHMP_FLAG_NAN     (1u << 6) /* non-finite prognostic state (added) */
+
+/* per-run scalars: the arguments of noahmp_sflx that do not vary per column (func:67-74) */
+typedef struct noahmp_run_params {
+  double julian0;   /* JULIAN at the first step; step s uses (float)(julian0 + s*dt/86400)        */
+  float  dt;        /* DT [s]                                                                      */
+  float  zsoil[4];  /* ZSOIL(1:4) [m], negative, layer bottoms                                     */
+  float  zref;      /* reference height of the forcing above the canopy/displacement height [m]   */
+  float  co2_frac;  /* CO2AIR = co2_frac * SFCPRS                                                  */
+  float  o2_frac;   /* O2AIR  = o2_frac  * SFCPRS                                                  */
+  float  foln;      /* FOLN [%]                                                                    */
+  int    yearlen;   /* YEARLEN [days]                                                              */
+} noahmp_run_params;
+
+/* ---- lifecycle: replaces engine:5-6 (noahmp_init) ---------------------------------------------- */
+int noahmp_init(noahmp_ctx** ctx, int device);
+int noahmp_finalize(noahmp_ctx* ctx);
+/* Run on this CUDA stream (a cudaStream_t passed as void*); NULL = the legacy default stream. */
+int noahmp_set_stream(noahmp_ctx* ctx, void* cuda_stream);
+const char* noahmp_last_error(const noahmp_ctx* ctx);
+
+/* ---- options: replaces noahmp_set_options, core/module_noahmp_global.f90:77-112, same order:
+ * veg, crs, btr, run, sfc, frz, inf, rad, alb, snf, tbot, stc.  Out-of-range values are rejected
+ * (< 0) except opt_veg, which the reference itself checks per column (func:375-378 -> FLAG_OPTVEG). */
+int noahmp_set_options(noahmp_ctx* ctx, const int opts[12]);
+
+/* ---- parameter tables: replaces noahmp_{gen,soil,veg}_param_readptable (gen_param:51, soil_param:31,
+ * veg_param:77).  The host parses the .TBL files and hands packed arrays:
+ *   gen    [NGEN]             slots of enum order CSOIL ZBOT CZIL DKREF KDTREF FRZK TIMEAN FSATMAX MLTFCT
+ *                             Z0SNO SSI SWEMAX ALBICE(2) ALBLAKE(2) OMEGAS(2) BETADS BETAIS EMSSOIL
+ *                             EMSLAKE NSLOPE SLOPE(30)
+ *   soil   [nsoiltyp][NSOILP] BEXP SMCMAX SMCREF SMCWLT PSISAT DKSAT DWSAT QUARTZ KDT FRZX
+ *   color  [ncolor][NCOLORP]  ALBSAT_VIS ALBSAT_NIR ALBDRY_VIS ALBDRY_NIR
+ *   veg_f  [nvegtyp][NVEGF]   RAD(9) PHYS(8) LAI12M(12) SAI12M(12) DVEG(8) PHOTO(22)
+ *   veg_i  [nvegtyp][NVEGI]   NROOT C3C4
+ *   flags  [5]                ISURBAN ISWATER ISBARREN ISICE ISEGBLF */
+int noahmp_set_tables(noahmp_ctx* ctx, const float* gen, int ngen, const float* soil, int nsoiltyp,
+                      const float* color, int ncolor, const float* veg_f, const int* veg_i, int nvegtyp,
+                      const int flags[5]);
+
+/* ---- the hot path: replaces engine:8-10 (noahmp_run) + the missing caller loop of func:66 --------
+ * Advance ncol columns by nsteps time steps on the context's stream (asynchronous).
+ *   state_dev    [NSTATE][ncol]  fp32 planes, in/out (ISNOW as int32 bits)
+ *   forcing_dev  step s at forcing_dev + s*forcing_step_stride, each [NFORCING][ncol]
+ *   static_f_dev [NSTATIC_F][ncol]; static_i_dev [ncol] packed types:
+ *                lutyp | sltyp<<8 | slptyp<<16 | ISC<<24 | (IST-1)<<28 | ICE<<29
+ *   diag_dev     [NDIAG][ncol] values of the LAST step, or NULL
+ *   budget_dev   [NBUDGET] fp64 sums accumulated (+=) over all columns and steps, or NULL          */
+int noahmp_run(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+               const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,
+               const int32_t* static_i_dev, float* diag_dev, double* budget_dev);
+
+/* Same call with HOST buffers: copies inputs to the device, runs, copies state (and diag/budget if
+ * non-NULL) back and synchronises.  forcing is [nsteps][NFORCING][ncol].  Returns the number of
+ * flagged columns (>= 0) or < 0.  This is the reference-facing entry a host driver binds. */
+int64_t noahmp_run_host(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state,
+                        const float* forcing, const float* static_f, const int32_t* static_i, float* diag,
+                        double* budget);
+
+/* ---- synthetic forcing generator (benchmark support; no counterpart in the reference) ------------
+ * Fills forcing_dev [NFORCING][ncol] for one step with the hash-based generator of
+ * noahmp_b200/synth.py (bit-identical).  sincos_dev [2][ncol] = sin(lat), cos(lat).
+ * coef[17] = synth.synth_params_array(); step_scalars[4] = sd, cdch, t_diur, t_seas. */
+int noahmp_synth_forcing(noahmp_ctx* ctx, int64_t ncol, int64_t col0, uint32_t seed, int step,
+                         const float* coef17, const float* step_scalars4, const float* sincos_dev,
+                         float* forcing_dev);
+
+/* ---- introspection ------------------------------------------------------------------------------ */
+int noahmp_layout(int what); /* 0 NSTATE 1 NSTATE_CORE 2 NFORCING 3 NSTATIC_F 4 NDIAG 5 NGEN 6 NSOILP
+                                7 NCOLORP 8 NVEGF 9 NVEGI 10 sizeof(noahmp_run_params) 11 NBUDGET */
+const char* noahmp_state_plane_name(int i);
+const char* noahmp_forcing_plane_name(int i);
+const char* noahmp_diag_plane_name(int i);
+const char* noahmp_budget_name(int i);
+/* kernels launched by this context since noahmp_init (for the benchmark's gpu_launches claim) */
+int64_t noahmp_launch_count(const noahmp_ctx* ctx);
+/* registers / local-memory bytes / static smem of the step kernel variant that `noahmp_run` would use */
+int noahmp_kernel_info(noahmp_ctx* ctx, int info[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOAHMP_B200_H */

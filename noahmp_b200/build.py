@@ -1,0 +1,74 @@
+"""Build the CUDA shared library in-tree (sm_100a only).
+
+    python -m noahmp_b200.build [--fast] [--force]
+
+* ``libnoahmp_b200.so``       parity build: ``-fmad=false`` -- every +,-,*,/ and sqrt is the same IEEE
+                              operation, in the same order, as the reference's fp32 Fortran; only libm
+                              calls (expf/logf/powf/...) may differ in the last ulp.
+* ``libnoahmp_b200_fast.so``  ``-fmad=true`` -- FMA contraction allowed (fewer instructions); same source.
+* ``libnoahmp_b200_strict.so`` ``-fmad=false -DNMP_CR_LIBM`` -- libm calls evaluated in fp64 and rounded once;
+                              must agree BIT FOR BIT with the oracle's ORACLE_CR_LIBM build (verification only).
+
+The built ``.so`` files are git-ignored but travel to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["noahmp_abi.cu"]
+HEADERS = ["common.cuh", "energy.cuh", "water.cuh", "column_step.cuh", os.path.join("..", "..", "include", "noahmp_b200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+VARIANTS = {"parity": ("libnoahmp_b200.so", ["-fmad=false"]),
+            "fast": ("libnoahmp_b200_fast.so", ["-fmad=true"]),
+            "strict": ("libnoahmp_b200_strict.so", ["-fmad=false", "-DNMP_CR_LIBM"])}
+
+
+def _variant(fast) -> str:
+    if isinstance(fast, str):
+        return fast
+    return "fast" if fast else "parity"
+
+
+def lib_path(fast=False) -> str:
+    override = os.environ.get("NOAHMP_B200_LIB")   # experiments only: absolute path of an alternative build
+    if override:
+        return override
+    return os.path.join(HERE, VARIANTS[_variant(fast)][0])
+
+
+def _stale(out: str) -> bool:
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_library(fast=False, force: bool = False, verbose: bool = False) -> str:
+    out = lib_path(fast)
+    if not force and not _stale(out):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *ARCH, "-lineinfo", "-O3", "-std=c++17", *VARIANTS[_variant(fast)][1],
+           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return out
+
+
+if __name__ == "__main__":
+    which = [v for v in VARIANTS if f"--{v}" in sys.argv] or ["parity"]
+    if "--all" in sys.argv:
+        which = list(VARIANTS)
+    for v in which:
+        print(build_library(fast=v, force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,313 @@
+// noahmp_b200 -- the step kernel: one thread advances one land column through nsteps time steps.
+//
+// Per step this is noahmp_sflx (core/module_noahmp_func.f90:66-476): atm (479-531), layer thickness,
+// root-zone temperature, phenology (534-630), energy, water, carbon, error (633-732) and the closing
+// fix-ups.  State is loaded from the structure-of-arrays planes once, kept in registers across all
+// steps of the launch (time fusion: only the 9 forcing planes are read per step) and stored once.
+#pragma once
+#include "water.cuh"
+
+namespace nmp {
+
+struct StepArgs {
+  float* state;           // [NSTATE][ncol]
+  const float* forcing;   // step s at forcing + s*forcing_stride, [NFORCING][ncol]
+  int64_t forcing_stride;
+  const float* static_f;  // [NSTATIC_F][ncol]
+  const int* static_i;    // [ncol]
+  float* diag;            // [NDIAG][ncol] or null
+  double* budget;         // [NBUDGET] or null
+  const Tables* tables;   // global copy, staged to shared memory
+  int64_t ncol;
+  int nsteps;
+  RunConst rc;
+  OptRuntime opt;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <class Opt, bool EXT, bool DIAG, bool BUDGET>
+#ifndef NMP_MIN_BLOCKS
+#define NMP_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(NMP_BLOCK, NMP_MIN_BLOCKS) column_step_kernel(const StepArgs a) {
+  __shared__ Tables T;
+  {  // stage the parameter tables (about 9.5 KB) into shared memory, coalesced
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < a.ncol;
+  const int64_t ii = active ? i : a.ncol - 1;   // tail threads shadow the last column, never store
+  const int64_t n = a.ncol;
+  const Opt opt(a.opt);
+  const RunConst& rc = a.rc;
+  const float DT = rc.dt;
+
+  // ---- load the column -------------------------------------------------------------------------
+  Column c;
+  {
+    const float* S = a.state + ii;
+    c.ALBOLD = S[S_ALBOLD * n]; c.SNEQVO = S[S_SNEQVO * n]; c.EAH = S[S_EAH * n]; c.FWET = S[S_FWET * n];
+    c.CANLIQ = S[S_CANLIQ * n]; c.CANICE = S[S_CANICE * n]; c.TV = S[S_TV * n]; c.TG = S[S_TG * n];
+    c.QSNOW = S[S_QSNOW * n]; c.ISNOW = __float_as_int(S[S_ISNOW * n]); c.snowh = S[S_SNOWH * n];
+    c.sneqv = S[S_SNEQV * n]; c.ZWT = S[S_ZWT * n]; c.WA = S[S_WA * n]; c.WT = S[S_WT * n]; c.TAUSS = S[S_TAUSS * n];
+static_for<0, (7) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.STC[k] = S[(S_STC + k) * n]; c.ZSNSO[k] = S[(S_ZSNSO + k) * n]; });
+static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.soilwat[k] = S[(S_SOILWAT + k) * n]; c.SMC[k] = S[(S_SMC + k) * n]; });
+static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.SNICE[k] = S[(S_SNICE + k) * n]; c.SNLIQ[k] = S[(S_SNLIQ + k) * n]; });
+    if (EXT) {
+      c.QSFC = S[S_QSFC * n]; c.TAH = S[S_TAH * n]; c.CM = S[S_CM * n]; c.CH = S[S_CH * n]; c.WSLAKE = S[S_WSLAKE * n];
+      c.LFMASS = S[S_LFMASS * n]; c.RTMASS = S[S_RTMASS * n]; c.STMASS = S[S_STMASS * n]; c.WOOD = S[S_WOOD * n];
+      c.STBLCP = S[S_STBLCP * n]; c.FASTCP = S[S_FASTCP * n]; c.LAI = S[S_LAI * n]; c.SAI = S[S_SAI * n];
+    } else {  // dead under the shipped option set: overwritten before any read
+      c.QSFC = 0.0f; c.TAH = 0.0f; c.CM = 0.0f; c.CH = 0.0f; c.WSLAKE = 0.0f; c.LFMASS = 0.0f; c.RTMASS = 0.0f;
+      c.STMASS = 0.0f; c.WOOD = 0.0f; c.STBLCP = 0.0f; c.FASTCP = 0.0f; c.LAI = 0.0f; c.SAI = 0.0f;
+    }
+    c.LAT = a.static_f[C_LAT * n + ii];
+    c.SHDFAC = a.static_f[C_SHDFAC * n + ii];
+    c.TBOT = a.static_f[C_TBOT * n + ii];
+    c.SHDMAX = (OptTraits<Opt>::runtime) ? a.static_f[C_SHDMAX * n + ii] : 0.0f;
+    const int ty = a.static_i[ii];
+    c.lutyp = ty & 0xff; c.sltyp = (ty >> 8) & 0xff; c.slptyp = (ty >> 16) & 0xff; c.ISC = (ty >> 24) & 0xf;
+    c.IST = ((ty >> 28) & 1) + 1; c.ICE = (ty >> 29) & 1;
+  }
+  const float* VG = &T.veg[(c.lutyp - 1) * NVEGF];
+  const int ISURBAN = T.flags[0], ISWATER = T.flags[1], ISBARREN = T.flags[2], ISICE = T.flags[3];
+  const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
+
+  DiagSink<DIAG> dg;
+  dg.base = DIAG ? a.diag + ii : nullptr;
+  dg.stride = n;
+  unsigned anyflag = 0;
+  double b_errwat = 0.0, b_errabs = 0.0, b_errmax = 0.0, b_fsa = 0.0, b_fsr = 0.0, b_fira = 0.0, b_fsh = 0.0, b_lh = 0.0;
+  double b_ssoil = 0.0, b_prcp = 0.0, b_et = 0.0, b_runoff = 0.0;
+
+#pragma unroll 1
+  for (int s = 0; s < a.nsteps; ++s) {
+    Forcing f;
+    {
+      const float* F = a.forcing + (int64_t)s * a.forcing_stride + ii;
+      f.SFCTMP = __ldg(F + F_SFCTMP * n); f.SFCPRS = __ldg(F + F_SFCPRS * n); f.UU = __ldg(F + F_UU * n);
+      f.VV = __ldg(F + F_VV * n); f.Q2 = __ldg(F + F_Q2 * n); f.SOLDN = __ldg(F + F_SOLDN * n);
+      f.LWDN = __ldg(F + F_LWDN * n); f.PRCP = __ldg(F + F_PRCP * n); f.COSZ = __ldg(F + F_COSZ * n);
+    }
+    const bool last = (s == a.nsteps - 1);
+    DiagSink<DIAG> dgs = dg;
+    if (DIAG && !last) dgs.base = nullptr;   // diagnostics of the last step only
+    const float JULIAN = (float)(rc.julian0 + (double)s * (double)DT / 86400.0);
+    unsigned flags = 0;
+
+  NMP_PHASE_SYNC();
+    // ---- atm, func:479-531 ------------------------------------------------------------------------
+    const float THAIR = f.SFCTMP * m_powf(f.SFCPRS / f.SFCPRS, RAIR / CPAIR);
+    const float QAIR = f.Q2;
+    const float EAIR = QAIR * f.SFCPRS / (0.622f + 0.378f * QAIR);
+    const float RHOAIR = (f.SFCPRS - 0.378f * EAIR) / (RAIR * f.SFCTMP);
+    const float QPRECC = 0.10f * f.PRCP, QPRECL = 0.90f * f.PRCP;
+    const float SWDOWN = (f.COSZ <= 0.0f) ? 0.0f : f.SOLDN;
+
+    // ---- FICEOLD (driver duty in the reference) and layer thickness, func:322-328 ------
+    float FICEOLD[3], DZSNSO[7];
+static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
+
+      FICEOLD[IX3(k)] = (k >= c.ISNOW + 1) ? c.SNICE[IX3(k)] / (c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)]) : 0.0f;
+    });
+static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      if (k == c.ISNOW + 1) DZSNSO[IX7(k)] = -c.ZSNSO[IX7(k)];
+      else if (k > c.ISNOW + 1) DZSNSO[IX7(k)] = c.ZSNSO[IX7(k > -2 ? k - 1 : k)] - c.ZSNSO[IX7(k)];
+      else DZSNSO[IX7(k)] = 0.0f;
+    });
+    // ---- root-zone temperature and initial water storage, func:332-344 ---------------------------
+    float TROOT = 0.0f;
+    {
+      const float zroot = -pick(rc.zsoil, NROOT - 1);
+static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+
+        if (k <= NROOT) TROOT = TROOT + c.STC[IX7(k)] * DZSNSO[IX7(k)] / zroot;
+      });
+    }
+    float BEG_WB = 0.0f;
+    if (c.IST == 1) {
+      BEG_WB = c.CANLIQ + c.CANICE + c.sneqv + c.WA;
+static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+ BEG_WB = BEG_WB + c.SMC[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
+      });
+    }
+    // ---- phenology, func:534-630 --------------------------------------------------------------------
+    float elai, esai, IGS, HTOP;
+    {
+      float LAI = c.LAI, SAI = c.SAI;
+      if (opt.veg == 1 || opt.veg == 3 || opt.veg == 4) {
+        const float ylen = (float)rc.yearlen;
+        const float DAY = (c.LAT >= 0.0f) ? JULIAN : fmodf(JULIAN + (0.5f * ylen), ylen);
+        const float Tm = 12.0f * DAY / ylen;
+        int IT1 = (int)(Tm + 0.5f);
+        int IT2 = IT1 + 1;
+        const float WT1 = ((float)IT1 + 0.5f) - Tm;
+        const float WT2 = 1.0f - WT1;
+        if (IT1 < 1) IT1 = 12;
+        if (IT2 > 12) IT2 = 1;
+        LAI = WT1 * VG[V_LAI12M + IT1 - 1] + WT2 * VG[V_LAI12M + IT2 - 1];
+        SAI = WT1 * VG[V_SAI12M + IT1 - 1] + WT2 * VG[V_SAI12M + IT2 - 1];
+      }
+      if (SAI < 0.05f) SAI = 0.0f;
+      if (LAI < 0.05f || SAI == 0.0f) LAI = 0.0f;
+      if ((c.lutyp == ISWATER) || (c.lutyp == ISBARREN) || (c.lutyp == ISICE) || (c.lutyp == ISURBAN)) { LAI = 0.0f; SAI = 0.0f; }
+      const float HVT = VG[V_HVT], HVB = VG[V_HVB];
+      const float DB = fmin2(fmax2(c.snowh - HVB, 0.0f), HVT - HVB);
+      float FB = DB / fmax2(1.0E-06f, HVT - HVB);
+      if (HVT > 0.0f && HVT <= 1.0f) {
+        const float snowhc = HVT * m_expf(-c.snowh / 0.2f);
+        FB = fmin2(c.snowh, snowhc) / snowhc;
+      }
+      elai = LAI * (1.0f - FB);
+      esai = SAI * (1.0f - FB);
+      if (esai < 0.05f) esai = 0.0f;
+      if (elai < 0.05f || esai == 0.0f) elai = 0.0f;
+      IGS = (c.TV > VG[V_TMIN]) ? 1.0f : 0.0f;
+      HTOP = HVT;
+      c.LAI = LAI;
+      c.SAI = SAI;
+    }
+    // ---- vegetation fraction, func:366-380 ----------------------------------------------------------
+    float fveg = 0.0f;
+    if (opt.veg == 1) { fveg = c.SHDFAC; if (fveg <= 0.01f) fveg = 0.01f; }
+    else if (opt.veg == 2 || opt.veg == 3) { fveg = 1.0f - m_expf(-0.52f * (c.LAI + c.SAI)); if (fveg <= 0.01f) fveg = 0.01f; }
+    else if (opt.veg == 4 || opt.veg == 5) { fveg = c.SHDMAX; if (fveg <= 0.01f) fveg = 0.01f; }
+    else flags |= FLAG_OPTVEG;
+    if (c.lutyp == ISURBAN || c.lutyp == ISBARREN) fveg = 0.0f;
+    if (elai + esai == 0.0f) fveg = 0.0f;
+
+    // ---- energy -------------------------------------------------------------------------------------
+    EnergyResult e;
+    energy<Opt, DIAG>(opt, T, rc, c, f, RHOAIR, QAIR, THAIR, EAIR, SWDOWN, IGS, HTOP, elai, esai, fveg, DZSNSO, e, dgs);
+    flags |= e.flags;
+
+    float soilice[4];
+static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
+ soilice[k] = fmax2(0.0f, c.SMC[k] - c.soilwat[k]);
+    });            // func:414
+    c.SNEQVO = c.sneqv;                                                                        // func:415
+    const float QVAP = fmax2(e.FGEV / e.LATHEAG, 0.0f);                                        // func:417-419
+    const float QDEW = fabsf(fmin2(e.FGEV / e.LATHEAG, 0.0f));
+    const float EDIR = QVAP - QDEW;
+
+  NMP_PHASE_SYNC();
+    // ---- water ----------------------------------------------------------------------------------------
+    WaterResult w;
+    water<Opt>(opt, T, rc, c, f, e, QPRECC, QPRECL, elai, esai, fveg, QVAP, QDEW, FICEOLD, soilice, DZSNSO, w);
+
+  NMP_PHASE_SYNC();
+    // ---- carbon, func:439-447 ---------------------------------------------------------------------------
+    float GPP = 0.0f, NPP = 0.0f, NEE = 0.0f;
+    if (OptTraits<Opt>::runtime) {
+      if (opt.veg == 2 || opt.veg == 5) carbon(T, rc, c, DZSNSO, e.PSN, e.BTRAN, IGS, GPP, NPP, NEE);
+    }
+
+    // ---- error, func:633-732: closure residuals become flag bits ---------------------------------------
+    const float ERRSW = SWDOWN - (e.FSA + e.FSR);
+    if (fabsf(ERRSW) > 0.01f) flags |= FLAG_ERRSW;
+    const float ERRENG = e.SAV + e.SAG - (e.FIRA + e.FSH + e.FCEV + e.FGEV + e.FCTR + e.SSOIL);
+    if (fabsf(ERRENG) > 0.01f) flags |= FLAG_ERRENG;
+    float ERRWAT = 0.0f;
+    if (c.IST == 1) {
+      float END_WB = c.CANLIQ + c.CANICE + c.sneqv + c.WA;
+static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+ END_WB = END_WB + c.SMC[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
+      });
+      ERRWAT = END_WB - BEG_WB - (f.PRCP - w.ECAN - w.ETRAN - EDIR - w.runsrf - w.runsub) * DT;
+    }
+    // ---- closing fix-ups, func:459-474 -------------------------------------------------------------------
+    float Q2B = e.Q2B;
+    if (c.lutyp == ISURBAN) {
+      const float QFX = w.ETRAN + w.ECAN + EDIR;
+      c.QSFC = (QFX / RHOAIR * e.CH_out) + QAIR;
+      Q2B = c.QSFC;
+    }
+    if (c.snowh <= 1.0E-6f || c.sneqv <= 1.0E-3f) { c.snowh = 0.0f; c.sneqv = 0.0f; }
+    const float ALBEDO = (SWDOWN != 0.0f) ? e.FSR / SWDOWN : -999.9f;
+
+    {  // added instrumentation: non-finite prognostics
+      bool bad = !isfinite(c.TV) || !isfinite(c.TG) || !isfinite(c.sneqv) || !isfinite(c.ZWT) || !isfinite(c.WA);
+static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+ bad = bad || !isfinite(c.STC[IX7(k)]) || !isfinite(c.SMC[IX4(k)]);
+      });
+      if (bad) flags |= FLAG_NAN;
+    }
+    anyflag |= flags;
+
+    if (DIAG) {
+      dgs.put(D_ECAN, w.ECAN); dgs.put(D_ETRAN, w.ETRAN); dgs.put(D_EDIR, EDIR); dgs.put(D_Q2B, Q2B);
+      dgs.put(D_RUNSRF, w.runsrf); dgs.put(D_RUNSUB, w.runsub); dgs.put(D_NEE, NEE); dgs.put(D_GPP, GPP);
+      dgs.put(D_NPP, NPP); dgs.put(D_FVEG, fveg); dgs.put(D_ALBEDO, ALBEDO); dgs.put(D_QSNBOT, w.QSNBOT);
+      dgs.put(D_PONDING1, w.PONDING1); dgs.put(D_PONDING2, w.PONDING2); dgs.put(D_FPICE, w.FPICE);
+      dgs.put(D_ERRWAT, ERRWAT); dgs.put(D_ERRSW, ERRSW); dgs.put(D_ERRENG, ERRENG);
+      dgs.puti(D_ITER, (e.iter_vege & 0xff) | ((e.iter_stom_sun & 0xff) << 8) | ((e.iter_stom_sha & 0xff) << 16) |
+                           ((w.niter_soil & 0xff) << 24));
+      dgs.puti(D_FLAGS, (int)anyflag);
+    }
+    if (BUDGET) {
+      b_errwat += (double)ERRWAT; b_errabs += fabs((double)ERRWAT); b_errmax = fmax(b_errmax, fabs((double)ERRWAT));
+      b_fsa += (double)e.FSA; b_fsr += (double)e.FSR; b_fira += (double)e.FIRA; b_fsh += (double)e.FSH;
+      b_lh += (double)(e.FCEV + e.FGEV + e.FCTR); b_ssoil += (double)e.SSOIL; b_prcp += (double)(f.PRCP * DT);
+      b_et += (double)((w.ECAN + w.ETRAN + EDIR) * DT); b_runoff += (double)((w.runsrf + w.runsub) * DT);
+    }
+  }
+
+  // ---- store the column -----------------------------------------------------------------------------
+  if (active) {
+    float* S = a.state + i;
+    S[S_ALBOLD * n] = c.ALBOLD; S[S_SNEQVO * n] = c.SNEQVO; S[S_EAH * n] = c.EAH; S[S_FWET * n] = c.FWET;
+    S[S_CANLIQ * n] = c.CANLIQ; S[S_CANICE * n] = c.CANICE; S[S_TV * n] = c.TV; S[S_TG * n] = c.TG;
+    S[S_QSNOW * n] = c.QSNOW; S[S_ISNOW * n] = __int_as_float(c.ISNOW); S[S_SNOWH * n] = c.snowh;
+    S[S_SNEQV * n] = c.sneqv; S[S_ZWT * n] = c.ZWT; S[S_WA * n] = c.WA; S[S_WT * n] = c.WT; S[S_TAUSS * n] = c.TAUSS;
+static_for<0, (7) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_STC + k) * n] = c.STC[k]; S[(S_ZSNSO + k) * n] = c.ZSNSO[k]; });
+static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_SOILWAT + k) * n] = c.soilwat[k]; S[(S_SMC + k) * n] = c.SMC[k]; });
+static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_SNICE + k) * n] = c.SNICE[k]; S[(S_SNLIQ + k) * n] = c.SNLIQ[k]; });
+    if (EXT) {
+      S[S_QSFC * n] = c.QSFC; S[S_TAH * n] = c.TAH; S[S_CM * n] = c.CM; S[S_CH * n] = c.CH; S[S_WSLAKE * n] = c.WSLAKE;
+      S[S_LFMASS * n] = c.LFMASS; S[S_RTMASS * n] = c.RTMASS; S[S_STMASS * n] = c.STMASS; S[S_WOOD * n] = c.WOOD;
+      S[S_STBLCP * n] = c.STBLCP; S[S_FASTCP * n] = c.FASTCP; S[S_LAI * n] = c.LAI; S[S_SAI * n] = c.SAI;
+    }
+  }
+
+  // ---- budget reduction: warp shuffle, one atomic per warp and quantity --------------------------------
+  if (BUDGET) {
+    const double on = active ? 1.0 : 0.0;
+    double soilw = 0.0;
+static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      const float thick = (k == 1) ? -rc.zsoil[0] : (rc.zsoil[k > 1 ? k - 2 : 0] - rc.zsoil[k - 1]);
+      soilw += (double)(c.SMC[IX4(k)] * thick * 1000.0f);
+    });
+    double v[NBUDGET];
+    v[B_NCELL] = on; v[B_NFLAGGED] = (anyflag != 0) ? on : 0.0; v[B_ERRWAT_SUM] = on * b_errwat;
+    v[B_ERRWAT_ABS] = on * b_errabs; v[B_ERRWAT_MAXABS] = on * b_errmax; v[B_FSA] = on * b_fsa; v[B_FSR] = on * b_fsr;
+    v[B_FIRA] = on * b_fira; v[B_FSH] = on * b_fsh; v[B_LH] = on * b_lh; v[B_SSOIL] = on * b_ssoil;
+    v[B_PRCP_DT] = on * b_prcp; v[B_ET_DT] = on * b_et; v[B_RUNOFF_DT] = on * b_runoff;
+    v[B_SNEQV] = on * (double)c.sneqv; v[B_SOILWATER] = on * soilw;
+static_for<0, (NBUDGET) - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
+      const double r = (q == B_ERRWAT_MAXABS) ? warp_max(v[q]) : warp_sum(v[q]);
+      if ((threadIdx.x & 31) == 0) {
+        if (q == B_ERRWAT_MAXABS) {
+          atomicMax(reinterpret_cast<unsigned long long*>(a.budget + q), (unsigned long long)__double_as_longlong(r));
+        } else {
+          atomicAdd(a.budget + q, r);
+        }
+      }
+    });
+  }
+}
+
+}  // namespace nmp

@@ -1,0 +1,353 @@
+// noahmp_b200 -- C ABI implementation (include/noahmp_b200.h): context, table upload, kernel dispatch,
+// the host-buffer entry point and the synthetic forcing generator.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/noahmp_b200.h"
+#include "column_step.cuh"
+
+using namespace nmp;
+
+static_assert(NSTATE == NOAHMP_NSTATE && NSTATE_CORE == NOAHMP_NSTATE_CORE && NFORCING == NOAHMP_NFORCING &&
+                  NSTATIC_F == NOAHMP_NSTATIC_F && NDIAG == NOAHMP_NDIAG && NBUDGET == NOAHMP_NBUDGET &&
+                  NGEN == NOAHMP_NGEN && NSOILP == NOAHMP_NSOILP && NCOLORP == NOAHMP_NCOLORP &&
+                  NVEGF == NOAHMP_NVEGF && NVEGI == NOAHMP_NVEGI,
+              "header and device layout disagree");
+
+struct noahmp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool have_opts = false, have_tables = false;
+  OptRuntime opt{};
+  bool opt_is_default = false;
+  Tables host_tables{};
+  Tables* dev_tables = nullptr;
+  double* dev_budget_scratch = nullptr;   // NBUDGET doubles
+  // grow-only staging buffers of noahmp_run_host
+  float* h_state = nullptr; float* h_forcing = nullptr; float* h_static_f = nullptr; int* h_static_i = nullptr;
+  float* h_diag = nullptr;
+  size_t cap_state = 0, cap_forcing = 0, cap_static_f = 0, cap_static_i = 0, cap_diag = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+const char* kStateNames[NSTATE] = {
+    "ALBOLD", "SNEQVO", "EAH", "FWET", "CANLIQ", "CANICE", "TV", "TG", "QSNOW", "ISNOW", "SNOWH", "SNEQV", "ZWT", "WA",
+    "WT", "TAUSS", "STC-2", "STC-1", "STC+0", "STC+1", "STC+2", "STC+3", "STC+4", "SOILWAT1", "SOILWAT2", "SOILWAT3",
+    "SOILWAT4", "SMC1", "SMC2", "SMC3", "SMC4", "ZSNSO-2", "ZSNSO-1", "ZSNSO+0", "ZSNSO+1", "ZSNSO+2", "ZSNSO+3",
+    "ZSNSO+4", "SNICE-2", "SNICE-1", "SNICE+0", "SNLIQ-2", "SNLIQ-1", "SNLIQ+0", "QSFC", "TAH", "CM", "CH", "WSLAKE",
+    "LFMASS", "RTMASS", "STMASS", "WOOD", "STBLCP", "FASTCP", "LAI", "SAI"};
+const char* kForcingNames[NFORCING] = {"SFCTMP", "SFCPRS", "UU", "VV", "Q2", "SOLDN", "LWDN", "PRCP", "COSZ"};
+const char* kDiagNames[NDIAG] = {
+    "FSA", "FSR", "FIRA", "FSH", "SSOIL", "FCEV", "FGEV", "FCTR", "ECAN", "ETRAN", "EDIR", "TRAD", "TGB", "TGV", "T2MV",
+    "T2MB", "Q2V", "Q2B", "RUNSRF", "RUNSUB", "APAR", "PSN", "SAV", "SAG", "FSNO", "NEE", "GPP", "NPP", "FVEG", "ALBEDO",
+    "QSNBOT", "PONDING", "PONDING1", "PONDING2", "RSSUN", "RSSHA", "BGAP", "WGAP", "CHV", "CHB", "EMISSI", "SHG", "SHC",
+    "SHB", "EVG", "EVB", "GHV", "GHB", "IRG", "IRC", "IRB", "TR", "EVC", "CHLEAF", "CHUC", "CHV2", "CHB2", "FPICE",
+    "ERRWAT", "ERRSW", "ERRENG", "ITER", "FLAGS"};
+const char* kBudgetNames[NBUDGET] = {"NCELL", "NFLAGGED", "ERRWAT_SUM", "ERRWAT_ABS", "ERRWAT_MAXABS", "FSA", "FSR",
+                                     "FIRA", "FSH", "LH", "SSOIL", "PRCP_DT", "ET_DT", "RUNOFF_DT", "SNEQV", "SOILWATER"};
+
+int fail(noahmp_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(noahmp_ctx* c, cudaError_t e, const char* where) {
+  return fail(c, -100 - (int)e, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(ctx, call)                                  \
+  do {                                                       \
+    cudaError_t _e = (call);                                 \
+    if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); \
+  } while (0)
+
+typedef void (*StepKernel)(const StepArgs);
+
+StepKernel pick_kernel(bool is_default, bool diag, bool budget) {
+  if (is_default) {
+    if (diag) return column_step_kernel<OptDefault, false, true, true>;
+    if (budget) return column_step_kernel<OptDefault, false, false, true>;
+    return column_step_kernel<OptDefault, false, false, false>;
+  }
+  if (diag) return column_step_kernel<OptRuntime, true, true, true>;
+  if (budget) return column_step_kernel<OptRuntime, true, false, true>;
+  return column_step_kernel<OptRuntime, true, false, false>;
+}
+
+// ---- synthetic forcing: integer hash + explicit round-to-nearest fp32 ops (no FMA contraction), so it
+// is bit-identical to noahmp_b200/synth.py: forcing_step ----------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ float uniform24(uint32_t key, uint32_t col) {
+  uint32_t h = mix32(col ^ key);
+  h = mix32(h + 0x27D4EB2Fu);
+  return __fmul_rn((float)(h >> 8), 1.0f / 16777216.0f);
+}
+struct SynthCoef {
+  float t_mean, t_lat, t_noise, sw_max, lw_mean, lw_tcoef, lw_noise, p_mean, p_noise, wind_min, wind_range, q_mean,
+      q_tcoef, q_noise, prcp_prob, inv_prob, prcp_scale;
+  float sd, cdch, t_diur, t_seas;
+  uint32_t seed;
+  int step;
+};
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define MUL(a, b) __fmul_rn((a), (b))
+__global__ void __launch_bounds__(256) synth_forcing_kernel(int64_t ncol, int64_t col0, SynthCoef p,
+                                                            const float* __restrict__ sincos,
+                                                            float* __restrict__ forcing) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  const uint32_t col = (uint32_t)(uint64_t)(col0 + i);
+  float u[12];
+#pragma unroll
+  for (int s = 0; s < 12; ++s) {
+    const uint32_t key = p.seed * 0x9E3779B1u + (uint32_t)p.step * 0x85EBCA77u + (uint32_t)s * 0xC2B2AE3Du;
+    u[s] = uniform24(key, col);
+  }
+  const float sinlat = sincos[i], coslat = sincos[ncol + i];
+  const float g1 = MUL(SUB(ADD(ADD(u[0], u[1]), ADD(u[2], u[3])), 2.0f), 1.7320508f);
+  const float g2 = MUL(SUB(ADD(ADD(u[4], u[5]), ADD(u[6], u[7])), 2.0f), 1.7320508f);
+  const float s2 = MUL(sinlat, sinlat);
+  const float tcore = ADD(ADD(p.t_mean, MUL(ADD(p.t_lat, p.t_seas), s2)), p.t_diur);
+  const float T = ADD(tcore, MUL(p.t_noise, g1));
+  const float cosz = ADD(MUL(sinlat, p.sd), MUL(coslat, p.cdch));
+  const float sw = MUL(p.sw_max, fmaxf(cosz, 0.0f));
+  const float lw = ADD(ADD(p.lw_mean, MUL(p.lw_tcoef, SUB(T, p.t_mean))), MUL(p.lw_noise, g2));
+  const float ps = ADD(p.p_mean, MUL(p.p_noise, SUB(MUL(2.0f, u[8]), 1.0f)));
+  const float wind = ADD(p.wind_min, MUL(p.wind_range, u[9]));
+  float e = fmaxf(ADD(1.0f, MUL(MUL(p.q_tcoef, SUB(tcore, p.t_mean)), 0.0625f)), 0.05f);
+  e = MUL(e, e); e = MUL(e, e); e = MUL(e, e); e = MUL(e, e);
+  float q = MUL(MUL(p.q_mean, e), ADD(1.0f, MUL(p.q_noise, SUB(MUL(2.0f, u[10]), 1.0f))));
+  q = fmaxf(q, 1.0e-4f);
+  const float ur = MUL(u[11], p.inv_prob);
+  const float pr = (u[11] < p.prcp_prob) ? MUL(p.prcp_scale, MUL(ur, ur)) : 0.0f;
+  forcing[F_SFCTMP * ncol + i] = T;
+  forcing[F_SFCPRS * ncol + i] = ps;
+  forcing[F_UU * ncol + i] = MUL(wind, 0.8f);
+  forcing[F_VV * ncol + i] = MUL(wind, 0.6f);
+  forcing[F_Q2 * ncol + i] = q;
+  forcing[F_SOLDN * ncol + i] = sw;
+  forcing[F_LWDN * ncol + i] = lw;
+  forcing[F_PRCP * ncol + i] = pr;
+  forcing[F_COSZ * ncol + i] = cosz;
+}
+
+int ensure(noahmp_ctx* c, void** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CUDA_TRY(c, cudaMalloc(p, need));
+  *cap = need;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int noahmp_init(noahmp_ctx** out, int device) {
+  if (!out) return -1;
+  *out = nullptr;
+  noahmp_ctx* c = new noahmp_ctx();
+  c->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "noahmp_init: cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e));
+    delete c;
+    return -100 - (int)e;
+  }
+  e = cudaMalloc(&c->dev_tables, sizeof(Tables));
+  if (e == cudaSuccess) e = cudaMalloc(&c->dev_budget_scratch, sizeof(double) * NBUDGET);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "noahmp_init: cudaMalloc: %s\n", cudaGetErrorString(e));
+    delete c;
+    return -100 - (int)e;
+  }
+  *out = c;
+  return 0;
+}
+
+int noahmp_finalize(noahmp_ctx* c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  cudaFree(c->dev_tables);
+  cudaFree(c->dev_budget_scratch);
+  cudaFree(c->h_state); cudaFree(c->h_forcing); cudaFree(c->h_static_f); cudaFree(c->h_static_i); cudaFree(c->h_diag);
+  delete c;
+  return 0;
+}
+
+int noahmp_set_stream(noahmp_ctx* c, void* s) {
+  if (!c) return -1;
+  c->stream = (cudaStream_t)s;
+  return 0;
+}
+
+const char* noahmp_last_error(const noahmp_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int noahmp_set_options(noahmp_ctx* c, const int o[12]) {
+  if (!c || !o) return -1;
+  // ranges of core/module_noahmp_global.f90:17-74; opt_veg is checked per column like the reference does
+  const int hi[12] = {1 << 30, 2, 3, 4, 2, 2, 2, 3, 2, 3, 2, 2};
+  const char* nm[12] = {"veg", "crs", "btr", "run", "sfc", "frz", "inf", "rad", "alb", "snf", "tbot", "stc"};
+  for (int k = 1; k < 12; ++k)
+    if (o[k] < 1 || o[k] > hi[k]) return fail(c, -2, std::string("option opt_") + nm[k] + " out of range");
+  c->opt = OptRuntime{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10], o[11]};
+  c->opt_is_default = o[0] == OptDefault::veg && o[1] == OptDefault::crs && o[2] == OptDefault::btr &&
+                      o[3] == OptDefault::run && o[4] == OptDefault::sfc && o[5] == OptDefault::frz &&
+                      o[6] == OptDefault::inf && o[7] == OptDefault::rad && o[8] == OptDefault::alb &&
+                      o[9] == OptDefault::snf && o[10] == OptDefault::tbot && o[11] == OptDefault::stc;
+  c->have_opts = true;
+  return 0;
+}
+
+int noahmp_set_tables(noahmp_ctx* c, const float* gen, int ngen, const float* soil, int nsoiltyp, const float* color,
+                      int ncolor, const float* veg_f, const int* veg_i, int nvegtyp, const int flags[5]) {
+  if (!c || !gen || !soil || !color || !veg_f || !veg_i || !flags) return -1;
+  if (ngen != NGEN) return fail(c, -3, "gen table must have NOAHMP_NGEN entries");
+  if (nsoiltyp < 1 || nsoiltyp > MAXSOILTYP) return fail(c, -3, "Table PARM is too big to be read");      // soil_param:48
+  if (ncolor < 1 || ncolor > MAXCOLOR) return fail(c, -3, "Table COLOR is too big to be read");           // soil_param:66
+  if (nvegtyp < 1 || nvegtyp > MAXVEGTYP) return fail(c, -3, "Table RAD is too big to be read");          // veg_param:97
+  Tables& t = c->host_tables;
+  std::memset(&t, 0, sizeof(t));
+  std::memcpy(t.gen, gen, sizeof(float) * NGEN);
+  std::memcpy(t.soil, soil, sizeof(float) * NSOILP * nsoiltyp);
+  std::memcpy(t.color, color, sizeof(float) * NCOLORP * ncolor);
+  std::memcpy(t.veg, veg_f, sizeof(float) * NVEGF * nvegtyp);
+  std::memcpy(t.vegi, veg_i, sizeof(int) * NVEGI * nvegtyp);
+  std::memcpy(t.flags, flags, sizeof(int) * 5);
+  t.nsoiltyp = nsoiltyp; t.ncolor = ncolor; t.nvegtyp = nvegtyp;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaMemcpy(c->dev_tables, &t, sizeof(Tables), cudaMemcpyHostToDevice));
+  c->have_tables = true;
+  return 0;
+}
+
+int noahmp_run(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+               const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,
+               const int32_t* static_i_dev, float* diag_dev, double* budget_dev) {
+  if (!c) return -1;
+  if (!c->have_opts) return fail(c, -4, "noahmp_set_options has not been called");
+  if (!c->have_tables) return fail(c, -4, "noahmp_set_tables has not been called");
+  if (!rp || !state_dev || !forcing_dev || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
+  if (ncol < 0 || nsteps < 0) return fail(c, -1, "negative size");
+  if (ncol == 0 || nsteps == 0) return 0;
+  if (!(rp->dt > 0.0f) || rp->yearlen <= 0) return fail(c, -5, "dt and yearlen must be positive");
+  for (int k = 0; k < 4; ++k)
+    if (!(rp->zsoil[k] < (k ? rp->zsoil[k - 1] : 0.0f))) return fail(c, -5, "zsoil must be negative and decreasing");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  StepArgs a;
+  a.state = state_dev; a.forcing = forcing_dev; a.forcing_stride = forcing_step_stride; a.static_f = static_f_dev;
+  a.static_i = static_i_dev; a.diag = diag_dev;
+  a.budget = budget_dev ? budget_dev : c->dev_budget_scratch;
+  a.tables = c->dev_tables; a.ncol = ncol; a.nsteps = nsteps;
+  a.rc.dt = rp->dt;
+  for (int k = 0; k < 4; ++k) a.rc.zsoil[k] = rp->zsoil[k];
+  a.rc.zref = rp->zref; a.rc.co2_frac = rp->co2_frac; a.rc.o2_frac = rp->o2_frac; a.rc.foln = rp->foln;
+  a.rc.yearlen = rp->yearlen; a.rc.julian0 = rp->julian0;
+  a.opt = c->opt;
+  StepKernel k = pick_kernel(c->opt_is_default, diag_dev != nullptr, budget_dev != nullptr);
+  const int block = NMP_BLOCK;
+  const int64_t grid = (ncol + block - 1) / block;
+  if (grid > 0x7fffffffLL) return fail(c, -6, "ncol too large for one launch");
+  k<<<(unsigned)grid, block, 0, c->stream>>>(a);
+  c->launches += 1;
+  CUDA_TRY(c, cudaGetLastError());
+  return 0;
+}
+
+int64_t noahmp_run_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state,
+                        const float* forcing, const float* static_f, const int32_t* static_i, float* diag,
+                        double* budget) {
+  if (!c) return -1;
+  if (!state || !forcing || !static_f || !static_i) return fail(c, -1, "null argument");
+  if (ncol <= 0 || nsteps <= 0) return 0;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)ncol;
+  const bool ext = !c->opt_is_default;
+  const size_t nplanes = ext ? NSTATE : NSTATE_CORE;   // the 13 extended planes are dead for the shipped options
+  int rc;
+  if ((rc = ensure(c, (void**)&c->h_state, &c->cap_state, sizeof(float) * NSTATE * n))) return rc;
+  if ((rc = ensure(c, (void**)&c->h_forcing, &c->cap_forcing, sizeof(float) * NFORCING * n * (size_t)nsteps))) return rc;
+  if ((rc = ensure(c, (void**)&c->h_static_f, &c->cap_static_f, sizeof(float) * NSTATIC_F * n))) return rc;
+  if ((rc = ensure(c, (void**)&c->h_static_i, &c->cap_static_i, sizeof(int) * n))) return rc;
+  if (diag && (rc = ensure(c, (void**)&c->h_diag, &c->cap_diag, sizeof(float) * NDIAG * n))) return rc;
+  cudaStream_t st = c->stream;
+  CUDA_TRY(c, cudaMemcpyAsync(c->h_state, state, sizeof(float) * nplanes * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->h_forcing, forcing, sizeof(float) * NFORCING * n * (size_t)nsteps, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->h_static_f, static_f, sizeof(float) * NSTATIC_F * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->h_static_i, static_i, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemsetAsync(c->dev_budget_scratch, 0, sizeof(double) * NBUDGET, st));
+  rc = noahmp_run(c, rp, ncol, nsteps, c->h_state, c->h_forcing, (int64_t)NFORCING * ncol, c->h_static_f, c->h_static_i,
+                  diag ? c->h_diag : nullptr, c->dev_budget_scratch);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemcpyAsync(state, c->h_state, sizeof(float) * nplanes * n, cudaMemcpyDeviceToHost, st));
+  if (diag) CUDA_TRY(c, cudaMemcpyAsync(diag, c->h_diag, sizeof(float) * NDIAG * n, cudaMemcpyDeviceToHost, st));
+  double b[NBUDGET];
+  CUDA_TRY(c, cudaMemcpyAsync(b, c->dev_budget_scratch, sizeof(double) * NBUDGET, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (budget) std::memcpy(budget, b, sizeof(b));
+  return (int64_t)llround(b[B_NFLAGGED]);
+}
+
+int noahmp_synth_forcing(noahmp_ctx* c, int64_t ncol, int64_t col0, uint32_t seed, int step, const float* coef17,
+                         const float* sc4, const float* sincos_dev, float* forcing_dev) {
+  if (!c || !coef17 || !sc4 || !sincos_dev || !forcing_dev) return -1;
+  if (ncol <= 0) return 0;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  SynthCoef p;
+  std::memcpy(&p, coef17, sizeof(float) * 17);
+  p.sd = sc4[0]; p.cdch = sc4[1]; p.t_diur = sc4[2]; p.t_seas = sc4[3];
+  p.seed = seed; p.step = step;
+  const int block = 256;
+  const int64_t grid = (ncol + block - 1) / block;
+  synth_forcing_kernel<<<(unsigned)grid, block, 0, c->stream>>>(ncol, col0, p, sincos_dev, forcing_dev);
+  c->launches += 1;
+  CUDA_TRY(c, cudaGetLastError());
+  return 0;
+}
+
+int noahmp_layout(int what) {
+  switch (what) {
+    case 0: return NSTATE;
+    case 1: return NSTATE_CORE;
+    case 2: return NFORCING;
+    case 3: return NSTATIC_F;
+    case 4: return NDIAG;
+    case 5: return NGEN;
+    case 6: return NSOILP;
+    case 7: return NCOLORP;
+    case 8: return NVEGF;
+    case 9: return NVEGI;
+    case 10: return (int)sizeof(noahmp_run_params);
+    case 11: return NBUDGET;
+  }
+  return -1;
+}
+const char* noahmp_state_plane_name(int i) { return (i >= 0 && i < NSTATE) ? kStateNames[i] : nullptr; }
+const char* noahmp_forcing_plane_name(int i) { return (i >= 0 && i < NFORCING) ? kForcingNames[i] : nullptr; }
+const char* noahmp_diag_plane_name(int i) { return (i >= 0 && i < NDIAG) ? kDiagNames[i] : nullptr; }
+const char* noahmp_budget_name(int i) { return (i >= 0 && i < NBUDGET) ? kBudgetNames[i] : nullptr; }
+int64_t noahmp_launch_count(const noahmp_ctx* c) { return c ? c->launches : -1; }
+
+int noahmp_kernel_info(noahmp_ctx* c, int info[4]) {
+  if (!c || !info) return -1;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaFuncAttributes at;
+  StepKernel k = pick_kernel(c->opt_is_default, false, false);
+  CUDA_TRY(c, cudaFuncGetAttributes(&at, (const void*)k));
+  info[0] = at.numRegs; info[1] = (int)at.localSizeBytes; info[2] = (int)at.sharedSizeBytes; info[3] = at.maxThreadsPerBlock;
+  return 0;
+}
+
+}  // extern "C"

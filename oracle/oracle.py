@@ -19,8 +19,15 @@ class RunParams(C.Structure):  # oracle/src/layout.h: struct RunParams
                 ("co2_frac", C.c_float), ("o2_frac", C.c_float), ("foln", C.c_float), ("yearlen", C.c_int)]
 
 
-def build(fast: bool = False) -> str:
-    target = "liboracle_fast.so" if fast else "liboracle.so"
+LIBS = {"parity": "liboracle.so", "fast": "liboracle_fast.so", "strict": "liboracle_cr.so"}
+
+
+def _variant(fast) -> str:
+    return fast if isinstance(fast, str) else ("fast" if fast else "parity")
+
+
+def build(fast=False) -> str:
+    target = LIBS[_variant(fast)]
     subprocess.run(["make", "-s", "-C", HERE, target], check=True)
     return os.path.join(HERE, target)
 
@@ -34,8 +41,8 @@ def _ip(a):
 
 
 class Oracle:
-    def __init__(self, tables, opts, fast: bool = False):
-        path = os.path.join(HERE, "liboracle_fast.so" if fast else "liboracle.so")
+    def __init__(self, tables, opts, fast=False):
+        path = os.path.join(HERE, LIBS[_variant(fast)])
         if not os.path.exists(path):
             path = build(fast)
         self.lib = lib = C.CDLL(path)

@@ -15,6 +15,26 @@
 #include <cstdint>
 #include <cstring>
 
+// ---- libm layer: with -DORACLE_CR_LIBM every fp32 libm call is evaluated in fp64 and rounded once
+// (correctly rounded except with probability ~2^-29).  The CUDA library has the same switch
+// (NMP_CR_LIBM); in that mode the two independent implementations must agree bit for bit.  The default
+// build keeps glibc's fp32 functions, i.e. what a gfortran build of the reference would call.
+#ifdef ORACLE_CR_LIBM
+namespace noahmp_oracle_cr {
+static inline float f1(double (*fn)(double), float x) { return (float)fn((double)x); }
+static inline float powf_(float x, float y) { return (float)std::pow((double)x, (double)y); }
+}  // namespace noahmp_oracle_cr
+#define expf(x) noahmp_oracle_cr::f1(std::exp, (x))
+#define logf(x) noahmp_oracle_cr::f1(std::log, (x))
+#define log10f(x) noahmp_oracle_cr::f1(std::log10, (x))
+#define tanhf(x) noahmp_oracle_cr::f1(std::tanh, (x))
+#define atanf(x) noahmp_oracle_cr::f1(std::atan, (x))
+#define tanf(x) noahmp_oracle_cr::f1(std::tan, (x))
+#define acosf(x) noahmp_oracle_cr::f1(std::acos, (x))
+#define cosf(x) noahmp_oracle_cr::f1(std::cos, (x))
+#define powf(x, y) noahmp_oracle_cr::powf_((x), (y))
+#endif
+
 namespace noahmp_oracle {
 
 // ---- dimensions: core/module_noahmp_global.f90:9-13
