@@ -5,7 +5,9 @@
 * ``libnoahmp_b200.so``       parity build: ``-fmad=false`` -- every +,-,*,/ and sqrt is the same IEEE
                               operation, in the same order, as the reference's fp32 Fortran; only libm
                               calls (expf/logf/powf/...) may differ in the last ulp.
-* ``libnoahmp_b200_fast.so``  ``-fmad=true`` -- FMA contraction allowed (fewer instructions); same source.
+* ``libnoahmp_b200_fast.so``  ``--use_fast_math`` -- FMA contraction, approximate division/sqrt and the MUFU-based
+                              __expf/__logf/__powf; 2.6x faster than the parity build and statistically as
+                              close to the oracle (the error floor is the physics' sensitivity, not the ulp).
 * ``libnoahmp_b200_strict.so`` ``-fmad=false -DNMP_CR_LIBM`` -- libm calls evaluated in fp64 and rounded once;
                               must agree BIT FOR BIT with the oracle's ORACLE_CR_LIBM build (verification only).
 
@@ -25,9 +27,17 @@ HEADERS = ["common.cuh", "energy.cuh", "water.cuh", "column_step.cuh", os.path.j
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
-VARIANTS = {"parity": ("libnoahmp_b200.so", ["-fmad=false"]),
-            "fast": ("libnoahmp_b200_fast.so", ["-fmad=true"]),
-            "strict": ("libnoahmp_b200_strict.so", ["-fmad=false", "-DNMP_CR_LIBM"])}
+# All variants are the SAME source.  NMP_PHASE_BARRIERS puts a CTA barrier at every phase boundary so the warps
+# of a CTA stay inside one instruction-cache window (the step is ~16k SASS instructions; without the
+# barriers ncu shows 70-80% of warp samples in stall_no_inst).  Block sizes were swept on B200
+# (profiles/r01_block_sweep.md): the IEEE builds want many warps in lock-step (768 threads, 80 registers,
+# spills absorbed by L1), the smaller fast-math code is best at 2 CTAs x 256 threads, 128 registers.
+COMMON = ["-DNMP_PHASE_BARRIERS"]
+VARIANTS = {
+    "parity": ("libnoahmp_b200.so", ["-fmad=false", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
+    "fast": ("libnoahmp_b200_fast.so", ["--use_fast_math", "-DNMP_BLOCK=256", "-DNMP_MIN_BLOCKS=2"]),
+    "strict": ("libnoahmp_b200_strict.so", ["-fmad=false", "-DNMP_CR_LIBM", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
+}
 
 
 def _variant(fast) -> str:
@@ -56,7 +66,7 @@ def build_library(fast=False, force: bool = False, verbose: bool = False) -> str
     if not force and not _stale(out):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *ARCH, "-lineinfo", "-O3", "-std=c++17", *VARIANTS[_variant(fast)][1],
+    cmd = [nvcc, *ARCH, "-lineinfo", "-O3", "-std=c++17", *COMMON, *VARIANTS[_variant(fast)][1],
            "-Xcompiler", "-fPIC", "-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")

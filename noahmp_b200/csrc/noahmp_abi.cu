@@ -239,9 +239,9 @@ int noahmp_run(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nst
   if (!c) return -1;
   if (!c->have_opts) return fail(c, -4, "noahmp_set_options has not been called");
   if (!c->have_tables) return fail(c, -4, "noahmp_set_tables has not been called");
-  if (!rp || !state_dev || !forcing_dev || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
   if (ncol < 0 || nsteps < 0) return fail(c, -1, "negative size");
-  if (ncol == 0 || nsteps == 0) return 0;
+  if (ncol == 0 || nsteps == 0) return 0;   // empty batch: nothing to do (an empty tensor has a null pointer)
+  if (!rp || !state_dev || !forcing_dev || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
   if (!(rp->dt > 0.0f) || rp->yearlen <= 0) return fail(c, -5, "dt and yearlen must be positive");
   for (int k = 0; k < 4; ++k)
     if (!(rp->zsoil[k] < (k ? rp->zsoil[k - 1] : 0.0f))) return fail(c, -5, "zsoil must be negative and decreasing");

@@ -1,0 +1,46 @@
+"""Multi-GPU layout of the column step: contiguous block partition, no halo, one tiny reduction.
+
+Columns share nothing but read-only tables (``noahmp_sflx`` is a one-column routine, func:66; ILOC/JLOC only
+feed messages), so each rank owns ``ceil(ncol/world)`` consecutive columns and the data path has NO
+collective.  The only exchange is the domain-mean water/energy budget: 15 fp64 sums + 1 fp64 max
+(``layout.BUDGET``), all-reduced over NCCL on GPUs (gloo in the CPU tests) at diagnostics cadence.
+"""
+from __future__ import annotations
+
+from . import layout as L
+
+
+def shard(ncol: int, rank: int, world: int) -> tuple[int, int]:
+    """(first column, column count) of ``rank``; trailing ranks may get fewer (or zero) columns."""
+    per = (ncol + world - 1) // world
+    c0 = min(rank * per, ncol)
+    return c0, min(c0 + per, ncol) - c0
+
+
+def allreduce_budget(budget, group=None):
+    """In-place all-reduce of a [NBUDGET] fp64 tensor: SUM for every slot except ERRWAT_MAXABS (MAX)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return budget
+    imax = L.B["ERRWAT_MAXABS"]
+    mx = budget[imax].clone()
+    budget[imax] = 0.0
+    dist.all_reduce(budget, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    budget[imax] = mx
+    return budget
+
+
+def budget_means(budget, nsteps: int) -> dict:
+    """Domain means per cell (and per step for fluxes) from the reduced sums."""
+    b = {n: float(budget[i]) for i, n in enumerate(L.BUDGET)}
+    n = max(b["NCELL"], 1.0)
+    out = {"cells": int(b["NCELL"]), "flagged": int(b["NFLAGGED"]), "errwat_mean_mm": b["ERRWAT_SUM"] / n / max(nsteps, 1),
+           "errwat_maxabs_mm": b["ERRWAT_MAXABS"]}
+    for k in ("FSA", "FSR", "FIRA", "FSH", "LH", "SSOIL"):
+        out[k.lower() + "_wm2"] = b[k] / n / max(nsteps, 1)
+    for k in ("PRCP_DT", "ET_DT", "RUNOFF_DT"):
+        out[k.lower().replace("_dt", "_mm")] = b[k] / n
+    out["sneqv_mm"] = b["SNEQV"] / n
+    out["soilwater_mm"] = b["SOILWATER"] / n
+    return out

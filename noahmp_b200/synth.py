@@ -314,7 +314,7 @@ def make_workload(name: str, ncol: int | None = None, nsteps: int | None = None,
         st = _blank_state(n)
         tsoil = [rng.uniform(268.0, 272.0, n).astype(f32) for _ in range(4)]
         smcmax = np.asarray(tables.soil["SMCMAX"], f32)[sltyp - 1]
-        fr = (f32(0.35) / smcmax).astype(f32)
+        fr = np.minimum(f32(0.35) / smcmax, f32(0.95)).astype(f32)   # SMC 0.35, but never above porosity (sand)
         _cold_start(st, tables, sltyp, tsoil, [fr, fr, fr, fr])
         for k in range(1, 5):
             st[L.soilwat(k)] = np.minimum(st[L.smc(k)], _supercool(tables, sltyp, st[L.stc(k)]))
