@@ -101,6 +101,17 @@ int64_t noahmp_run_host(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t nc
                         const float* forcing, const float* static_f, const int32_t* static_i, float* diag,
                         double* budget);
 
+/* Streaming variant for a time-marching driver: the column state and the static planes STAY on the device
+ * (uploaded once, like a model's weights), only the forcing arrives from the host.  Forcing of launch k+1 is
+ * copied H2D on a private copy stream into a double buffer while launch k computes (`steps_per_launch` model
+ * steps per launch, >= 1).  forcing_host is [nsteps][NFORCING][ncol] and should be page-locked for the copies
+ * to overlap.  budget_host (nullable) receives the 16 budget sums of this call.  Synchronises before returning
+ * the number of column-launches that raised a flag (>= 0; a column flagged in m launches counts m times) or
+ * < 0 on error. */
+int64_t noahmp_advance_host(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t ncol, int nsteps,
+                            float* state_dev, const float* forcing_host, const float* static_f_dev,
+                            const int32_t* static_i_dev, double* budget_host, int steps_per_launch);
+
 /* ---- synthetic forcing generator (benchmark support; no counterpart in the reference) ------------
  * Fills forcing_dev [NFORCING][ncol] for one step with the hash-based generator of
  * noahmp_b200/synth.py (bit-identical).  sincos_dev [2][ncol] = sin(lat), cos(lat).

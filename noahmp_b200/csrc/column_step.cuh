@@ -20,6 +20,7 @@ struct StepArgs {
   const Tables* tables;   // global copy, staged to shared memory
   int64_t ncol;
   int nsteps;
+  int final_launch;       // 1: add the end-of-launch budget slots (NCELL, SNEQV, SOILWATER)
   RunConst rc;
   OptRuntime opt;
 };
@@ -286,17 +287,18 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(
   // ---- budget reduction: warp shuffle, one atomic per warp and quantity --------------------------------
   if (BUDGET) {
     const double on = active ? 1.0 : 0.0;
+    const double fin = (active && a.final_launch) ? 1.0 : 0.0;
     double soilw = 0.0;
 static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       const float thick = (k == 1) ? -rc.zsoil[0] : (rc.zsoil[k > 1 ? k - 2 : 0] - rc.zsoil[k - 1]);
       soilw += (double)(c.SMC[IX4(k)] * thick * 1000.0f);
     });
     double v[NBUDGET];
-    v[B_NCELL] = on; v[B_NFLAGGED] = (anyflag != 0) ? on : 0.0; v[B_ERRWAT_SUM] = on * b_errwat;
+    v[B_NCELL] = fin; v[B_NFLAGGED] = (anyflag != 0) ? on : 0.0; v[B_ERRWAT_SUM] = on * b_errwat;
     v[B_ERRWAT_ABS] = on * b_errabs; v[B_ERRWAT_MAXABS] = on * b_errmax; v[B_FSA] = on * b_fsa; v[B_FSR] = on * b_fsr;
     v[B_FIRA] = on * b_fira; v[B_FSH] = on * b_fsh; v[B_LH] = on * b_lh; v[B_SSOIL] = on * b_ssoil;
     v[B_PRCP_DT] = on * b_prcp; v[B_ET_DT] = on * b_et; v[B_RUNOFF_DT] = on * b_runoff;
-    v[B_SNEQV] = on * (double)c.sneqv; v[B_SOILWATER] = on * soilw;
+    v[B_SNEQV] = fin * (double)c.sneqv; v[B_SOILWATER] = fin * soilw;
 static_for<0, (NBUDGET) - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
       const double r = (q == B_ERRWAT_MAXABS) ? warp_max(v[q]) : warp_sum(v[q]);
       if ((threadIdx.x & 31) == 0) {

@@ -32,6 +32,11 @@ struct noahmp_ctx {
   float* h_state = nullptr; float* h_forcing = nullptr; float* h_static_f = nullptr; int* h_static_i = nullptr;
   float* h_diag = nullptr;
   size_t cap_state = 0, cap_forcing = 0, cap_static_f = 0, cap_static_i = 0, cap_diag = 0;
+  // noahmp_advance_host: copy stream, double-buffered forcing, hand-off events
+  cudaStream_t copy_stream = nullptr;
+  float* fbuf[2] = {nullptr, nullptr};
+  size_t cap_fbuf = 0;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int64_t launches = 0;
   std::string err;
 };
@@ -183,6 +188,12 @@ int noahmp_finalize(noahmp_ctx* c) {
   cudaFree(c->dev_tables);
   cudaFree(c->dev_budget_scratch);
   cudaFree(c->h_state); cudaFree(c->h_forcing); cudaFree(c->h_static_f); cudaFree(c->h_static_i); cudaFree(c->h_diag);
+  cudaFree(c->fbuf[0]); cudaFree(c->fbuf[1]);
+  for (int k = 0; k < 2; ++k) {
+    if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
+    if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
   return 0;
 }
@@ -233,9 +244,9 @@ int noahmp_set_tables(noahmp_ctx* c, const float* gen, int ngen, const float* so
   return 0;
 }
 
-int noahmp_run(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
-               const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,
-               const int32_t* static_i_dev, float* diag_dev, double* budget_dev) {
+static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+                    const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,
+                    const int32_t* static_i_dev, float* diag_dev, double* budget_dev, int final_launch) {
   if (!c) return -1;
   if (!c->have_opts) return fail(c, -4, "noahmp_set_options has not been called");
   if (!c->have_tables) return fail(c, -4, "noahmp_set_tables has not been called");
@@ -250,7 +261,7 @@ int noahmp_run(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nst
   a.state = state_dev; a.forcing = forcing_dev; a.forcing_stride = forcing_step_stride; a.static_f = static_f_dev;
   a.static_i = static_i_dev; a.diag = diag_dev;
   a.budget = budget_dev ? budget_dev : c->dev_budget_scratch;
-  a.tables = c->dev_tables; a.ncol = ncol; a.nsteps = nsteps;
+  a.tables = c->dev_tables; a.ncol = ncol; a.nsteps = nsteps; a.final_launch = final_launch;
   a.rc.dt = rp->dt;
   for (int k = 0; k < 4; ++k) a.rc.zsoil[k] = rp->zsoil[k];
   a.rc.zref = rp->zref; a.rc.co2_frac = rp->co2_frac; a.rc.o2_frac = rp->o2_frac; a.rc.foln = rp->foln;
@@ -264,6 +275,13 @@ int noahmp_run(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nst
   c->launches += 1;
   CUDA_TRY(c, cudaGetLastError());
   return 0;
+}
+
+int noahmp_run(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+               const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,
+               const int32_t* static_i_dev, float* diag_dev, double* budget_dev) {
+  return run_impl(c, rp, ncol, nsteps, state_dev, forcing_dev, forcing_step_stride, static_f_dev, static_i_dev, diag_dev,
+                  budget_dev, 1);
 }
 
 int64_t noahmp_run_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state,
@@ -298,6 +316,62 @@ int64_t noahmp_run_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol
   CUDA_TRY(c, cudaStreamSynchronize(st));
   if (budget) std::memcpy(budget, b, sizeof(b));
   return (int64_t)llround(b[B_NFLAGGED]);
+}
+
+int64_t noahmp_advance_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+                            const float* forcing_host, const float* static_f_dev, const int32_t* static_i_dev,
+                            double* budget_host, int steps_per_launch) {
+  if (!c) return -1;
+  if (ncol <= 0 || nsteps <= 0) return 0;
+  if (!rp || !state_dev || !forcing_host || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int g = steps_per_launch > 0 ? (steps_per_launch < nsteps ? steps_per_launch : nsteps) : 1;
+  const size_t step_words = (size_t)NFORCING * (size_t)ncol;
+  if (!c->copy_stream) {
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    }
+  }
+  const size_t need = sizeof(float) * step_words * (size_t)g;
+  if (need > c->cap_fbuf) {
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    for (int k = 0; k < 2; ++k) {
+      if (c->fbuf[k]) cudaFree(c->fbuf[k]);
+      c->fbuf[k] = nullptr;
+    }
+    c->cap_fbuf = 0;
+    CUDA_TRY(c, cudaMalloc((void**)&c->fbuf[0], need));
+    CUDA_TRY(c, cudaMalloc((void**)&c->fbuf[1], need));
+    c->cap_fbuf = need;
+  }
+  cudaStream_t cs = c->stream;   // compute stream
+  CUDA_TRY(c, cudaMemsetAsync(c->dev_budget_scratch, 0, sizeof(double) * NBUDGET, cs));
+  // the copy stream must not overwrite a buffer an earlier call on the compute stream may still read
+  CUDA_TRY(c, cudaEventRecord(c->ev_done[0], cs));
+  CUDA_TRY(c, cudaEventRecord(c->ev_done[1], cs));
+  int chunk = 0;
+  for (int s0 = 0; s0 < nsteps; s0 += g, ++chunk) {
+    const int n = (nsteps - s0 < g) ? nsteps - s0 : g;
+    const int b = chunk & 1;
+    CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->fbuf[b], forcing_host + (size_t)s0 * step_words, sizeof(float) * step_words * (size_t)n,
+                                cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_copied[b], 0));
+    noahmp_run_params r = *rp;
+    r.julian0 = rp->julian0 + (double)s0 * (double)rp->dt / 86400.0;
+    const int rc = run_impl(c, &r, ncol, n, state_dev, c->fbuf[b], (int64_t)step_words, static_f_dev, static_i_dev, nullptr,
+                            c->dev_budget_scratch, s0 + g >= nsteps ? 1 : 0);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev_done[b], cs));
+  }
+  double bsum[NBUDGET];
+  CUDA_TRY(c, cudaMemcpyAsync(bsum, c->dev_budget_scratch, sizeof(double) * NBUDGET, cudaMemcpyDeviceToHost, cs));
+  CUDA_TRY(c, cudaStreamSynchronize(cs));
+  if (budget_host) std::memcpy(budget_host, bsum, sizeof(bsum));
+  return (int64_t)llround(bsum[B_NFLAGGED]);
 }
 
 int noahmp_synth_forcing(noahmp_ctx* c, int64_t ncol, int64_t col0, uint32_t seed, int step, const float* coef17,

@@ -116,6 +116,16 @@ class NoahMP:
                                                     _host_ptr(forcing), _host_ptr(static_f), _host_ptr(static_i),
                                                     _host_ptr(diag), _host_ptr(budget)), "noahmp_run_host")
 
+    def advance_host(self, rp: RunParams, state, forcing_host, static_f, static_i, budget=None, steps_per_launch: int = 1) -> int:
+        """``noahmp_advance_host``: device-resident ``state``/``static_*`` (CUDA tensors), forcing streamed from a
+        (pinned) host buffer [nsteps,9,ncol] through a double buffer, H2D overlapped with compute.  ``budget``: host
+        fp64 array/tensor [16] or None.  Returns the flagged column-launch count."""
+        nsteps, nf, ncol = forcing_host.shape
+        assert nf == L.NFORCING and tuple(state.shape) == (L.NSTATE, ncol)
+        return self._check(self.lib.noahmp_advance_host(self.ctx, C.byref(rp), ncol, nsteps, _dev_ptr(state),
+                                                        _host_ptr(forcing_host), _dev_ptr(static_f), _dev_ptr(static_i),
+                                                        _host_ptr(budget), int(steps_per_launch)), "noahmp_advance_host")
+
     def synth_forcing(self, ncol, col0, seed, step, coef17: np.ndarray, scalars4: np.ndarray, sincos, out) -> None:
         self._check(self.lib.noahmp_synth_forcing(self.ctx, ncol, col0, seed, step, _fp(coef17), _fp(scalars4),
                                                   _dev_ptr(sincos), _dev_ptr(out)), "noahmp_synth_forcing")

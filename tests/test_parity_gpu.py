@@ -222,6 +222,30 @@ def test_host_entry_point_equals_device_entry_point(tables):
     eng.close()
 
 
+def test_streaming_entry_point_equals_device_entry_point(tables):
+    """noahmp_advance_host (state resident, forcing streamed from the host through a double buffer) == noahmp_run,
+    for several launch granularities, and its budget sums match (end-of-launch slots counted once)."""
+    w = synth.make_workload("snow1m", ncol=5000, nsteps=13)
+    forcing = synth.forcing_all(w)
+    gs, _, gb = gpu_run(tables, w, forcing, "parity")
+    eng = NoahMP(tables, w.opts)
+    rp = eng.run_params(w.dt, synth.ZSOIL, w.julian0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
+    sf, si = torch.from_numpy(w.static_f).to(DEV), torch.from_numpy(w.static_i).to(DEV)
+    hf = torch.from_numpy(forcing).pin_memory()
+    for g in (1, 4, 13, 50):
+        st = torch.from_numpy(w.state.copy()).to(DEV)
+        bd = np.zeros(L.NBUDGET)
+        l0 = eng.launch_count()
+        assert eng.advance_host(rp, st, hf, sf, si, bd, g) == 0
+        assert eng.launch_count() - l0 == -(-w.nsteps // min(g, w.nsteps))
+        assert np.array_equal(st.cpu().numpy()[:L.NSTATE_CORE].view(np.int32), gs[:L.NSTATE_CORE].view(np.int32)), g
+        assert bd[L.B["NCELL"]] == w.ncol
+        for k in ("FSA", "FIRA", "FSH", "LH", "SSOIL", "PRCP_DT", "ET_DT", "RUNOFF_DT", "SNEQV", "SOILWATER", "ERRWAT_ABS"):
+            assert np.isclose(bd[L.B[k]], gb[L.B[k]], rtol=1e-9, atol=1e-6), (g, k)
+        assert bd[L.B["ERRWAT_MAXABS"]] == gb[L.B["ERRWAT_MAXABS"]]
+    eng.close()
+
+
 def test_step_fusion_equals_step_by_step(tables):
     """One launch of N fused steps == N launches of one step (state round-trips through HBM in between)."""
     w = synth.make_workload("snow1m", ncol=2048, nsteps=10)
