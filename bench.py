@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from noahmp_b200 import layout as L, synth  # noqa: E402
-from noahmp_b200.parallel import allreduce_budget, budget_means, shard  # noqa: E402
+from noahmp_b200.parallel import allreduce_budget, budget_means, divergence_order, shard  # noqa: E402
 from noahmp_b200.tables import ParamTables  # noqa: E402
 
 B_ALG = 404  # algorithmic bytes per cell-step (SURVEY 8d / DESIGN.md section 4)
@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--ncol", type=int, default=None, help="override the workload's TOTAL column count")
     ap.add_argument("--model-steps", type=int, default=None, help="override model time steps per launch")
     ap.add_argument("--variant", default="fast", choices=["parity", "fast", "strict"])
+    ap.add_argument("--no-sort-columns", action="store_true", help="keep the generator's random column order")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps-per-launch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -105,6 +106,14 @@ def measured_peak_gbs():
 
 def build_workload(args):
     w = synth.make_workload(args.workload, ncol=args.ncol, nsteps=args.model_steps)
+    if not args.no_sort_columns:
+        # divergence-class ordering, balanced over the ranks; done once at set-up
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        order = divergence_order(w.static_i, w.static_f[L.C["LAT"]], world)
+        w.state = np.ascontiguousarray(w.state[:, order])
+        w.static_f = np.ascontiguousarray(w.static_f[:, order])
+        w.static_i = np.ascontiguousarray(w.static_i[order])
+        w.sincos = np.ascontiguousarray(w.sincos[:, order])
     return w
 
 
@@ -317,6 +326,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w.name, "columns": w.ncol, "columns_per_gpu": nloc, "model_steps_per_step": w.nsteps,
                            "dt_s": w.dt, "options": w.opts, "variant": args.variant, "partition": f"block x{world}",
+                           "column_order": "random (generator)" if args.no_sort_columns else "land-use type, latitude band; dealt round-robin to ranks",
                            "l2": "inputs larger than L2 (state+forcing per launch >> 126 MB); no flush needed"
                                  if nloc * 4 * (2 * 44 + 9 * w.nsteps) > 2 * 126e6 else "inputs fit L2: traffic is L2-resident",
                            "kernel": eng.kernel_info()},

@@ -400,6 +400,114 @@ __device__ __forceinline__ void twostream_band(const TwoStreamCommon& t, int IC,
   o.FAB = 1.0f - o.FRE - (1.0f - ALBGRD) * o.FTD - (1.0f - ALBGRI) * o.FTI;               // func:2454-2455
 }
 
+// ---- the canopy Newton loop ("loop1", func:2744-2877) as a relocatable object ------------------------
+// Everything one pass of the loop reads or writes for one column, so a column's iteration can be handed to
+// another thread of the CTA (tail compaction, see energy()).  first() = sfcdif1|2 + ragrb (func:3260-3350) +
+// esat(TV); second() = canopy-air closure, fluxes, Newton update and the exit test.  The stomata call of pass 1
+// sits between the two halves in the caller.
+struct Loop1 {
+  // per-column constants of the loop
+  float SFCTMP, RHOAIR, QAIR, ZLVL, ZPD, Z0M, UR, TMPCM, TMPCH, TMPCM2, TMPCH2, Z0MG, CWP, VAIE, HCAN, rbfac, TGV, FWET,
+      LAISUNE, LAISHAE, RSSUN, RSSHA, RSURF, EAIR, ESTG, GAMMAV, fveg, AIR, CIR, SAV, SFCPRS, evcap_liq, evcap_ice, THAIR, CZIL;
+  // evolving
+  MoninObukhov mo;
+  float WSTAR, H, HG, FHG, TAH, EAH, TV;
+  int LITER, iter_done, running;
+  // produced by the last pass
+  float RAHC, RAHG, RB, ESTV, DESTV, CAH, CVH, IRC, SHC, EVC, TR, QSFC;
+
+  template <class Opt>
+  __device__ __forceinline__ void first(const Opt& opt, int iter) {
+    if (opt.sfc == 1) sfcdif1(iter, SFCTMP, RHOAIR, H, QAIR, ZLVL, ZPD, Z0M, UR, TMPCM, TMPCH, TMPCM2, TMPCH2, mo);
+    if (opt.sfc == 2) {                                                                   // func:2763-2772
+      sfcdif2(iter, Z0M, TAH, THAIR, UR, CZIL, ZLVL, mo.CM, mo.CH, mo.MOZ, WSTAR, mo.FV);
+      mo.CH = mo.CH / UR;
+      mo.CM = mo.CM / UR;
+    }
+    RAHC = fmax2(1.0f, 1.0f / (mo.CH * UR));                                              // func:2774-2776
+    // ragrb, func:3260-3350 (Z0H = Z0M, Z0HG = Z0MG: func:2746-2752)
+    float MOZG = 0.0f;
+    if (iter > 1) {
+      float TMP1 = KARMAN * (GRAV / TAH) * HG / (RHOAIR * CPAIR);
+      if (fabsf(TMP1) <= MPE) TMP1 = MPE;
+      const float MOLG = -1.0f * cube(mo.FV) / TMP1;
+      MOZG = fmin2((ZPD - Z0MG) / MOLG, 1.0f);
+    }
+    const float FHGNEW = (MOZG < 0.0f) ? m_powf(1.0f - 15.0f * MOZG, -0.25f) : 1.0f + 4.7f * MOZG;
+    FHG = (iter == 1) ? FHGNEW : 0.5f * (FHG + FHGNEW);
+    const float CWPC = m_powf(CWP * VAIE * HCAN * FHG, 0.5f);
+    const float TMP1 = m_expf(-CWPC * Z0MG / HCAN);
+    const float TMP2 = m_expf(-CWPC * (Z0M + ZPD) / HCAN);
+    const float TMPRAH2 = HCAN * m_expf(CWPC) / CWPC * (TMP1 - TMP2);
+    const float KH = fmax2(KARMAN * mo.FV * (HCAN - ZPD), MPE);
+    RAHG = TMPRAH2 / KH;
+    const float TMPRB = CWPC * 50.0f / (1.0f - m_expf(-CWPC / 2.0f));
+    RB = TMPRB * rbfac;
+    const float Tc = tdc(TV);                                                             // func:2787-2795
+    float ESATW, ESATI, DSATW, DSATI;
+    esat(Tc, ESATW, ESATI, DSATW, DSATI);
+    if (Tc > 0.0f) { ESTV = ESATW; DESTV = DSATW; } else { ESTV = ESATI; DESTV = DSATI; }
+  }
+
+  __device__ __forceinline__ void second(int iter) {
+    CAH = 1.0f / RAHC;                                                                    // func:2817-2823
+    const float RAWC = RAHC, RAWG = RAHG;
+    CVH = 2.0f * VAIE / RB;
+    const float CGH = 1.0f / RAHG;
+    float COND = CAH + CVH + CGH;
+    const float ATA = (SFCTMP * CAH + TGV * CGH) / COND;
+    const float BTA = CVH / COND;
+    const float CSH = (1.0f - BTA) * RHOAIR * CPAIR * CVH;
+    const float CAW = 1.0f / RAWC;                                                        // func:2826-2834
+    const float CEW = FWET * VAIE / RB;
+    const float CTW = (1.0f - FWET) * (LAISUNE / (RB + RSSUN) + LAISHAE / (RB + RSSHA));
+    const float CGW = 1.0f / (RAWG + RSURF);
+    COND = CAW + CEW + CTW + CGW;
+    const float AEA = (EAIR * CAW + ESTG * CGW) / COND;
+    const float BEA = (CEW + CTW) / COND;
+    const float CEV = (1.0f - BEA) * CEW * RHOAIR * CPAIR / GAMMAV;
+    const float CTR = (1.0f - BEA) * CTW * RHOAIR * CPAIR / GAMMAV;
+    TAH = ATA + BTA * TV;                                                                 // func:2837-2838
+    EAH = AEA + BEA * ESTV;
+    IRC = fveg * (AIR + CIR * pow4(TV));                                                  // func:2840-2848
+    SHC = fveg * RHOAIR * CPAIR * CVH * (TV - TAH);
+    EVC = fveg * RHOAIR * CPAIR * CEW * (ESTV - EAH) / GAMMAV;
+    TR = fveg * RHOAIR * CPAIR * CTW * (ESTV - EAH) / GAMMAV;
+    if (TV > TFRZ) EVC = fmin2(evcap_liq, EVC);
+    else EVC = fmin2(evcap_ice, EVC);
+    const float B = SAV - IRC - SHC - EVC - TR;                                           // func:2850-2852
+    const float A = fveg * (4.0f * CIR * cube(TV) + CSH + (CEV + CTR) * DESTV);
+    const float DTV = B / A;
+    IRC = IRC + fveg * 4.0f * CIR * cube(TV) * DTV;                                       // func:2854-2860
+    SHC = SHC + fveg * CSH * DTV;
+    EVC = EVC + fveg * CEV * DESTV * DTV;
+    TR = TR + fveg * CTR * DESTV * DTV;
+    TV = TV + DTV;
+    H = RHOAIR * CPAIR * (TAH - SFCTMP) / RAHC;                                           // func:2864-2868
+    HG = RHOAIR * CPAIR * (TGV - TAH) / RAHG;
+    QSFC = (0.622f * EAH) / (SFCPRS - 0.378f * EAH);
+    iter_done = iter;
+    if (LITER == 1) running = 0;                                                          // func:2870-2875
+    else if (iter >= 5 && fabsf(DTV) <= 0.01f) LITER = 1;
+  }
+};
+// field lists for the shared-memory hand-off (member-wise, so the struct itself stays in registers)
+#define NMP_LOOP1_FLOATS(X)                                                                                          \
+  X(SFCTMP) X(RHOAIR) X(QAIR) X(ZLVL) X(ZPD) X(Z0M) X(UR) X(TMPCM) X(TMPCH) X(TMPCM2) X(TMPCH2) X(Z0MG) X(CWP) X(VAIE)  \
+  X(HCAN) X(rbfac) X(TGV) X(FWET) X(LAISUNE) X(LAISHAE) X(RSSUN) X(RSSHA) X(RSURF) X(EAIR) X(ESTG) X(GAMMAV) X(fveg)   \
+  X(AIR) X(CIR) X(SAV) X(SFCPRS) X(evcap_liq) X(evcap_ice) X(THAIR) X(CZIL) X(mo.MOZ) X(mo.FM) X(mo.FH) X(mo.FM2)       \
+  X(mo.FH2) X(mo.FV) X(mo.CM) X(mo.CH) X(mo.CH2) X(WSTAR) X(H) X(HG) X(FHG) X(TAH) X(EAH) X(TV) X(RAHC) X(RAHG) X(RB)   \
+  X(ESTV) X(DESTV) X(CAH) X(CVH) X(IRC) X(SHC) X(EVC) X(TR) X(QSFC)
+#define NMP_LOOP1_INTS(X) X(mo.MOZSGN) X(LITER) X(iter_done) X(running)
+#define NMP_COUNT(f) +1
+constexpr int LOOP1_WORDS = 0 NMP_LOOP1_FLOATS(NMP_COUNT) NMP_LOOP1_INTS(NMP_COUNT);
+static_assert(LOOP1_WORDS * 4 == sizeof(Loop1), "hand-off field lists must cover every member of Loop1");
+// Slots of the CTA-shared hand-off buffer: about 17% of the vegetated columns need more than the 6 mandatory
+// passes, so 3/8 of the CTA is ample; overflow lanes simply keep iterating in place.
+#ifdef NMP_COMPACT_LOOP1
+constexpr int LOOP1_CAP = (NMP_BLOCK * 3 / 8) < 136 ? (NMP_BLOCK * 3 / 8) : 136;   // static smem stays below 48 KB
+#endif
+
 // =====================================================================================================
 // energy: func:735-1338 with its callees thermoprop/csnow (1341-1497), radiation/albedo/surrad/snowage/
 // snowalb_*/groundalb (1598-2212), vege_flux (2465-2964), bare_flux (2967-3257), ragrb (3260-3350),
@@ -687,147 +795,168 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   MoninObukhov mo;
   mo.MOZ = 0.0f; mo.FM = 0.0f; mo.FH = 0.0f; mo.FM2 = 0.0f; mo.FH2 = 0.0f; mo.FV = 0.1f; mo.CM = c.CM; mo.CH = c.CH;
   mo.CH2 = 0.0f; mo.MOZSGN = 0;
-  float WSTAR = 0.0f, HG = 0.0f, H = 0.0f, MOZG = 0.0f, FHG = 0.0f, RAHG = 0.0f, RAWG = 0.0f, RB = 0.0f;
-  float ESATW, ESATI, DSATW, DSATI, ESTG = 0.0f, ESTV = 0.0f, DESTV = 0.0f, CAH = 0.0f, CVH = 0.0f;
-  float VAIE = 0.0f, LAISUNE = 0.0f, LAISHAE = 0.0f, HCAN = HTOP, UC = 0.0f, AIR = 0.0f, CIR = 0.0f;
-  float TMPCM = 0.0f, TMPCH = 0.0f, TMPCM2 = 0.0f, TMPCH2 = 0.0f, rbfac = 0.0f, RAHC = 1.0f;
+  float RAHG = 0.0f, RAWG = 0.0f;
+  float ESATW, ESATI, DSATW, DSATI, ESTG = 0.0f, CAH = 0.0f, CVH = 0.0f;
+  float HCAN = HTOP, AIR = 0.0f, CIR = 0.0f;
   float CSH = 0.0f, CEV = 0.0f, CGH = 0.0f;
-  const float Z0H = Z0M, Z0HG = Z0MG;                                                     // func:2746-2752
+  const float Z0H = Z0M;                                                                  // func:2746-2752
   LeafParams LP;
   LP.BP = VG[V_BP]; LP.MP = VG[V_MP]; LP.FOLNMX = VG[V_FOLNMX]; LP.QE25 = VG[V_QE25]; LP.KC25 = VG[V_KC25];
   LP.AKC = VG[V_AKC]; LP.KO25 = VG[V_KO25]; LP.AKO = VG[V_AKO]; LP.VCMX25 = VG[V_VCMX25]; LP.AVCMX = VG[V_AVCMX];
   LP.C3C4 = T.vegi[(c.lutyp - 1) * NVEGI + VI_C3C4];
+  Loop1 L;
+  L.mo = mo; L.WSTAR = 0.0f; L.H = 0.0f; L.HG = 0.0f; L.FHG = 0.0f; L.TAH = TAH; L.EAH = EAH; L.TV = TV;
+  L.LITER = 0; L.iter_done = 0; L.running = veg_tile ? 1 : 0;
+  L.RAHC = 1.0f; L.RAHG = 0.0f; L.RB = 0.0f; L.ESTV = 0.0f; L.DESTV = 0.0f; L.CAH = 0.0f; L.CVH = 0.0f; L.IRC = 0.0f;
+  L.SHC = 0.0f; L.EVC = 0.0f; L.TR = 0.0f; L.QSFC = QSFC;
+  L.SFCTMP = f.SFCTMP; L.RHOAIR = RHOAIR; L.QAIR = QAIR; L.ZLVL = ZLVL; L.ZPD = ZPD; L.Z0M = Z0M; L.UR = UR;
+  L.TMPCM = 0.0f; L.TMPCH = 0.0f; L.TMPCM2 = 0.0f; L.TMPCH2 = 0.0f; L.Z0MG = Z0MG; L.CWP = CWP; L.VAIE = 0.0f; L.HCAN = HCAN;
+  L.rbfac = 0.0f; L.TGV = c.TG; L.FWET = c.FWET; L.LAISUNE = 0.0f; L.LAISHAE = 0.0f; L.RSSUN = 0.0f; L.RSSHA = 0.0f;
+  L.RSURF = RSURF; L.EAIR = EAIR; L.ESTG = 0.0f; L.GAMMAV = GAMMAV; L.fveg = fveg; L.AIR = 0.0f; L.CIR = 0.0f; L.SAV = SAV;
+  L.SFCPRS = f.SFCPRS; L.evcap_liq = c.CANLIQ * LATHEAV / DT; L.evcap_ice = c.CANICE * LATHEAV / DT; L.THAIR = THAIR;
+  L.CZIL = T.gen[G_CZIL];
   if (veg_tile) {
     TGV = c.TG;
     CMV = c.CM;
     CHV = c.CH;
-    VAIE = fmin2(6.0f, VAI / fveg);                                                       // func:2704-2706
-    LAISUNE = fmin2(6.0f, LAISUN / fveg);
-    LAISHAE = fmin2(6.0f, LAISHA / fveg);
+    L.VAIE = fmin2(6.0f, VAI / fveg);                                                     // func:2704-2706
+    L.LAISUNE = fmin2(6.0f, LAISUN / fveg);
+    L.LAISHAE = fmin2(6.0f, LAISHA / fveg);
     const float Tc = tdc(TGV);                                                            // func:2710-2716
     esat(Tc, ESATW, ESATI, DSATW, DSATI);
     ESTG = (Tc > 0.0f) ? ESATW : ESATI;
-    QSFC = 0.622f * EAIR / (PSFC - 0.378f * EAIR);                                        // func:2720
-    UC = UR * m_logf(HCAN / Z0M) / m_logf(ZLVL / Z0M);                                    // func:2725
+    L.ESTG = ESTG;
+    L.QSFC = 0.622f * EAIR / (PSFC - 0.378f * EAIR);                                      // func:2720
+    const float UC = UR * m_logf(HCAN / Z0M) / m_logf(ZLVL / Z0M);                        // func:2725
     if ((HCAN - ZPD) <= 0.0f) r.flags |= FLAG_HCAN;                                       // func:2726-2738
     if (ZLVL <= ZPD) r.flags |= FLAG_ZLVL;                                                // func:3412-3415
-    AIR = -EMV * (1.0f + (1.0f - EMV) * (1.0f - EMG)) * f.LWDN - EMV * EMG * SB * pow4(TGV);  // func:2741-2742
-    CIR = (2.0f - EMV * (1.0f - EMG)) * EMV * SB;
-    TMPCM = m_logf((ZLVL - ZPD) / Z0M); TMPCH = m_logf((ZLVL - ZPD) / Z0H);               // func:3417-3420
-    TMPCM2 = m_logf((2.0f + Z0M) / Z0M); TMPCH2 = m_logf((2.0f + Z0H) / Z0H);
-    rbfac = sqrtf(VG[V_DLEAF] / UC);                                                      // func:3347 (loop invariant)
+    L.AIR = -EMV * (1.0f + (1.0f - EMV) * (1.0f - EMG)) * f.LWDN - EMV * EMG * SB * pow4(TGV);  // func:2741-2742
+    L.CIR = (2.0f - EMV * (1.0f - EMG)) * EMV * SB;
+    L.TMPCM = m_logf((ZLVL - ZPD) / Z0M); L.TMPCH = m_logf((ZLVL - ZPD) / Z0H);           // func:3417-3420
+    L.TMPCM2 = m_logf((2.0f + Z0M) / Z0M); L.TMPCH2 = m_logf((2.0f + Z0H) / Z0H);
+    L.rbfac = sqrtf(VG[V_DLEAF] / UC);                                                    // func:3347 (loop invariant)
   }
+  // ---- loop1, func:2744-2877.  The exit test cannot fire before the end of pass 6 (LITER is set at
+  // pass >= 5 and acts one pass later), so passes 1..6 run for every canopy column; the data-dependent tail
+  // (passes 7..20, ~17% of the columns) is what makes warps diverge.
+#pragma unroll 1
+  for (int iter = 1; iter <= 6; ++iter) {
+    if (L.running) L.first(opt, iter);
+    if (iter == 1) {                                                                      // func:2798-2814
+      if (opt.crs == 1) {
+#pragma unroll 1
+        for (int leaf = 0; leaf < 2; ++leaf) {
+          Stomata sm;
+          sm.done = true; sm.niter = 0; sm.rs = 0.0f; sm.psn = 0.0f;
+          if (L.running) sm.begin(LP, f.SFCPRS, f.SFCTMP, leaf ? PARSHA : PARSUN, L.TV, O2AIR, CO2AIR, rc.foln, BTRAN, L.RB);
+#pragma unroll 1
+          for (int bis = 0; bis < 20; ++bis) {
+            if (!(L.running && !sm.done)) break;
+            sm.step(LP, IGS, f.SFCPRS, L.EAH, L.ESTV, CO2AIR);
+          }
+          if (L.running) {
+            if (leaf == 0) { RSSUN = sm.rs; PSNSUN = sm.psn; r.iter_stom_sun = sm.niter; }
+            else { RSSHA = sm.rs; PSNSHA = sm.psn; r.iter_stom_sha = sm.niter; }
+          }
+        }
+      }
+      if (opt.crs == 2) {
+        if (L.running) {
+          canres(VG[V_RGL], VG[V_RSMIN], VG[V_RSMAX], VG[V_TOPT], VG[V_HS], f.SFCPRS, L.TV, PARSUN, L.EAH, BTRAN, RSSUN, PSNSUN);
+          canres(VG[V_RGL], VG[V_RSMIN], VG[V_RSMAX], VG[V_TOPT], VG[V_HS], f.SFCPRS, L.TV, PARSHA, L.EAH, BTRAN, RSSHA, PSNSHA);
+        }
+      }
+      L.RSSUN = RSSUN;
+      L.RSSHA = RSSHA;
+    }
+    if (L.running) L.second(iter);
+  }
+#ifdef NMP_COMPACT_LOOP1
   {
-    int LITER = 0;
-    bool running = veg_tile;
+    // ---- tail compaction: columns that still iterate after pass 6 are packed into the first warps of the
+    // CTA through shared memory, so the tail runs on full warps instead of a few lanes per warp.
+    __shared__ float xch[LOOP1_WORDS][LOOP1_CAP];
+    __shared__ int xcnt;
+    if (threadIdx.x == 0) xcnt = 0;
+    __syncthreads();
+    const unsigned ball = __ballot_sync(0xffffffffu, L.running != 0);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ball) base = atomicAdd(&xcnt, __popc(ball));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int slot = base + __popc(ball & ((1u << lane) - 1u));
+    const bool moved = (L.running != 0) && slot < LOOP1_CAP;
+    if (moved) {
+      int w = 0;
+#define X(fld) xch[w++][slot] = L.fld;
+      NMP_LOOP1_FLOATS(X)
+#undef X
+#define X(fld) xch[w++][slot] = __int_as_float(L.fld);
+      NMP_LOOP1_INTS(X)
+#undef X
+      L.running = 0;
+    }
+    __syncthreads();
+    const int njobs = xcnt < LOOP1_CAP ? xcnt : LOOP1_CAP;
 #pragma unroll 1
-    for (int iter = 1; iter <= 20; ++iter) {                                              // loop1, func:2744-2877
-      if (!NMP_ANY(running)) break;
-      if (running) {
-        r.iter_vege = iter;
-        if (opt.sfc == 1) {
-          sfcdif1(iter, f.SFCTMP, RHOAIR, H, QAIR, ZLVL, ZPD, Z0H, UR, TMPCM, TMPCH, TMPCM2, TMPCH2, mo);
-        }
-        if (opt.sfc == 2) {                                                               // func:2763-2772
-          sfcdif2(iter, Z0M, TAH, THAIR, UR, T.gen[G_CZIL], ZLVL, mo.CM, mo.CH, mo.MOZ, WSTAR, mo.FV);
-          mo.CH = mo.CH / UR;
-          mo.CM = mo.CM / UR;
-        }
-        RAHC = fmax2(1.0f, 1.0f / (mo.CH * UR));                                          // func:2774-2776
+    for (int job = 0; job < 2; ++job) {
+      // job 0: a packed column from the hand-off buffer; job 1: this thread's own column if it overflowed
+      const bool work = (job == 0) ? ((int)threadIdx.x < njobs) : (L.running != 0);
+      if (!__any_sync(0xffffffffu, work)) continue;
+      Loop1 W = L;
+      if (job == 0 && work) {
+        int w = 0;
+#define X(fld) W.fld = xch[w++][threadIdx.x];
+        NMP_LOOP1_FLOATS(X)
+#undef X
+#define X(fld) W.fld = __float_as_int(xch[w++][threadIdx.x]);
+        NMP_LOOP1_INTS(X)
+#undef X
       }
-      NMP_LOOP_SYNC();
-      if (running) {
-        // ragrb, func:3260-3350
-        MOZG = 0.0f;
-        if (iter > 1) {
-          float TMP1 = KARMAN * (GRAV / TAH) * HG / (RHOAIR * CPAIR);
-          if (fabsf(TMP1) <= MPE) TMP1 = MPE;
-          const float MOLG = -1.0f * cube(mo.FV) / TMP1;
-          MOZG = fmin2((ZPD - Z0MG) / MOLG, 1.0f);
-        }
-        const float FHGNEW = (MOZG < 0.0f) ? m_powf(1.0f - 15.0f * MOZG, -0.25f) : 1.0f + 4.7f * MOZG;
-        FHG = (iter == 1) ? FHGNEW : 0.5f * (FHG + FHGNEW);
-        const float CWPC = m_powf(CWP * VAIE * HCAN * FHG, 0.5f);
-        const float TMP1 = m_expf(-CWPC * Z0HG / HCAN);
-        const float TMP2 = m_expf(-CWPC * (Z0H + ZPD) / HCAN);
-        const float TMPRAH2 = HCAN * m_expf(CWPC) / CWPC * (TMP1 - TMP2);
-        const float KH = fmax2(KARMAN * mo.FV * (HCAN - ZPD), MPE);
-        RAHG = TMPRAH2 / KH;
-        RAWG = RAHG;
-        const float TMPRB = CWPC * 50.0f / (1.0f - m_expf(-CWPC / 2.0f));
-        RB = TMPRB * rbfac;
-        const float Tc = tdc(TV);                                                         // func:2787-2795
-        esat(Tc, ESATW, ESATI, DSATW, DSATI);
-        if (Tc > 0.0f) { ESTV = ESATW; DESTV = DSATW; } else { ESTV = ESATI; DESTV = DSATI; }
-      }
-      if (iter == 1) {                                                                    // func:2798-2814
-        if (opt.crs == 1) {
+      if (!work) W.running = 0;
 #pragma unroll 1
-          for (int leaf = 0; leaf < 2; ++leaf) {
-            NMP_LOOP_SYNC();
-            Stomata sm;
-            sm.done = true; sm.niter = 0; sm.rs = 0.0f; sm.psn = 0.0f;
-            if (running) sm.begin(LP, f.SFCPRS, f.SFCTMP, leaf ? PARSHA : PARSUN, TV, O2AIR, CO2AIR, rc.foln, BTRAN, RB);
-#pragma unroll 1
-            for (int bis = 0; bis < 20; ++bis) {
-              if (!NMP_ANY(running && !sm.done)) break;
-              if (running && !sm.done) sm.step(LP, IGS, f.SFCPRS, EAH, ESTV, CO2AIR);
-            }
-            if (running) {
-              if (leaf == 0) { RSSUN = sm.rs; PSNSUN = sm.psn; r.iter_stom_sun = sm.niter; }
-              else { RSSHA = sm.rs; PSNSHA = sm.psn; r.iter_stom_sha = sm.niter; }
-            }
-          }
-        }
-        if (opt.crs == 2) {
-          if (running) {
-            canres(VG[V_RGL], VG[V_RSMIN], VG[V_RSMAX], VG[V_TOPT], VG[V_HS], f.SFCPRS, TV, PARSUN, EAH, BTRAN, RSSUN, PSNSUN);
-            canres(VG[V_RGL], VG[V_RSMIN], VG[V_RSMAX], VG[V_TOPT], VG[V_HS], f.SFCPRS, TV, PARSHA, EAH, BTRAN, RSSHA, PSNSHA);
-          }
-        }
+      for (int iter = 7; iter <= 20; ++iter) {
+        if (!W.running) break;
+        W.first(opt, iter);
+        W.second(iter);
       }
-      NMP_LOOP_SYNC();
-      if (running) {
-        CAH = 1.0f / RAHC;                                                                // func:2817-2823
-        const float RAWC = RAHC;
-        CVH = 2.0f * VAIE / RB;
-        CGH = 1.0f / RAHG;
-        float COND = CAH + CVH + CGH;
-        const float ATA = (f.SFCTMP * CAH + TGV * CGH) / COND;
-        const float BTA = CVH / COND;
-        CSH = (1.0f - BTA) * RHOAIR * CPAIR * CVH;
-        const float CAW = 1.0f / RAWC;                                                    // func:2826-2834
-        const float CEW = c.FWET * VAIE / RB;
-        const float CTW = (1.0f - c.FWET) * (LAISUNE / (RB + RSSUN) + LAISHAE / (RB + RSSHA));
-        const float CGW = 1.0f / (RAWG + RSURF);
-        COND = CAW + CEW + CTW + CGW;
-        const float AEA = (EAIR * CAW + ESTG * CGW) / COND;
-        const float BEA = (CEW + CTW) / COND;
-        CEV = (1.0f - BEA) * CEW * RHOAIR * CPAIR / GAMMAV;
-        const float CTR = (1.0f - BEA) * CTW * RHOAIR * CPAIR / GAMMAV;
-        TAH = ATA + BTA * TV;                                                             // func:2837-2838
-        EAH = AEA + BEA * ESTV;
-        IRC = fveg * (AIR + CIR * pow4(TV));                                              // func:2840-2848
-        SHC = fveg * RHOAIR * CPAIR * CVH * (TV - TAH);
-        EVC = fveg * RHOAIR * CPAIR * CEW * (ESTV - EAH) / GAMMAV;
-        TR = fveg * RHOAIR * CPAIR * CTW * (ESTV - EAH) / GAMMAV;
-        if (TV > TFRZ) EVC = fmin2(c.CANLIQ * LATHEAV / DT, EVC);
-        else EVC = fmin2(c.CANICE * LATHEAV / DT, EVC);
-        const float B = SAV - IRC - SHC - EVC - TR;                                       // func:2850-2852
-        const float A = fveg * (4.0f * CIR * cube(TV) + CSH + (CEV + CTR) * DESTV);
-        const float DTV = B / A;
-        IRC = IRC + fveg * 4.0f * CIR * cube(TV) * DTV;                                   // func:2854-2860
-        SHC = SHC + fveg * CSH * DTV;
-        EVC = EVC + fveg * CEV * DESTV * DTV;
-        TR = TR + fveg * CTR * DESTV * DTV;
-        TV = TV + DTV;
-        H = RHOAIR * CPAIR * (TAH - f.SFCTMP) / RAHC;                                     // func:2864-2868
-        HG = RHOAIR * CPAIR * (TGV - TAH) / RAHG;
-        QSFC = (0.622f * EAH) / (f.SFCPRS - 0.378f * EAH);
-        if (LITER == 1) running = false;                                                  // func:2870-2875
-        else if (iter >= 5 && fabsf(DTV) <= 0.01f) LITER = 1;
+      if (work) {
+        if (job == 0) {
+          int w = 0;
+#define X(fld) xch[w++][threadIdx.x] = W.fld;
+          NMP_LOOP1_FLOATS(X)
+#undef X
+#define X(fld) xch[w++][threadIdx.x] = __int_as_float(W.fld);
+          NMP_LOOP1_INTS(X)
+#undef X
+        } else {
+          L = W;
+        }
       }
     }
+    __syncthreads();
+    if (moved) {
+      int w = 0;
+#define X(fld) L.fld = xch[w++][slot];
+      NMP_LOOP1_FLOATS(X)
+#undef X
+#define X(fld) L.fld = __float_as_int(xch[w++][slot]);
+      NMP_LOOP1_INTS(X)
+#undef X
+    }
+  }
+#else
+#pragma unroll 1
+  for (int iter = 7; iter <= 20; ++iter) {
+    if (!L.running) break;
+    L.first(opt, iter);
+    L.second(iter);
+  }
+#endif
+  if (veg_tile) {
+    r.iter_vege = L.iter_done;
+    mo = L.mo; TAH = L.TAH; EAH = L.EAH; TV = L.TV; RAHG = L.RAHG; RAWG = L.RAHG; CAH = L.CAH; CVH = L.CVH;
+    IRC = L.IRC; SHC = L.SHC; EVC = L.EVC; TR = L.TR; QSFC = L.QSFC; AIR = L.AIR; CIR = L.CIR;
   }
   NMP_PHASE_SYNC();
   // under-canopy ground temperature, loop2, func:2881-2914

@@ -17,6 +17,29 @@ def shard(ncol: int, rank: int, world: int) -> tuple[int, int]:
     return c0, min(c0 + per, ncol) - c0
 
 
+def divergence_order(static_i, lat, world: int = 1, chunk: int = 32768):
+    """Permutation of the columns that (a) groups them by divergence class -- land-use type (canopy tile on/off,
+    table rows), then latitude band (day/night, phenology month) -- so the 32 lanes of a warp take the same
+    branches, and (b) deals the sorted sequence to ``world`` ranks in round-robin chunks, so the contiguous block
+    partition of :func:`shard` gives every rank the same class mix (cheap barren columns are not all on one GPU).
+    Columns are independent (func:66 is a one-column routine), so their order is the driver's choice; apply the
+    permutation once to state/static planes at set-up and invert it on output."""
+    import numpy as np
+    static_i = np.asarray(static_i)
+    lut = (static_i & 0xff).astype(np.int64)
+    band = np.clip(((np.asarray(lat, np.float64) + 1.6) * 20.0).astype(np.int64), 0, 63)
+    order = np.argsort(lut * 64 + band, kind="stable")
+    if world <= 1:
+        return order
+    n = order.size
+    nchunk = (n + chunk - 1) // chunk
+    owner = np.arange(nchunk) % world
+    pieces = [[] for _ in range(world)]
+    for k in range(nchunk):
+        pieces[owner[k]].append(order[k * chunk:(k + 1) * chunk])
+    return np.concatenate([np.concatenate(p) if p else np.empty(0, order.dtype) for p in pieces])
+
+
 def allreduce_budget(budget, group=None):
     """In-place all-reduce of a [NBUDGET] fp64 tensor: SUM for every slot except ERRWAT_MAXABS (MAX)."""
     import torch.distributed as dist

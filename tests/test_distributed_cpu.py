@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from conftest import ROOT
 from noahmp_b200 import layout as L, synth
-from noahmp_b200.parallel import allreduce_budget, budget_means, shard
+from noahmp_b200.parallel import allreduce_budget, budget_means, divergence_order, shard
 
 
 def test_shard_covers_everything_once():
@@ -21,6 +21,25 @@ def test_shard_covers_everything_once():
             assert sum(n for _, n in parts) == ncol
             assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             assert max(n for _, n in parts) - min(n for _, n in parts if n or world <= ncol) <= (ncol + world - 1) // world
+
+
+def test_divergence_order_is_a_balanced_permutation():
+    w = synth.make_workload("conus1km", ncol=200_000, nsteps=1)
+    lat = w.static_f[L.C["LAT"]]
+    for world in (1, 2, 8):
+        order = divergence_order(w.static_i, lat, world, chunk=512)
+        assert np.array_equal(np.sort(order), np.arange(w.ncol))
+        lut = (w.static_i & 0xff)[order]
+        if world == 1:
+            assert (np.diff(lut) >= 0).all()                       # grouped by land-use type
+        shares = []
+        for r in range(world):
+            c0, n = shard(w.ncol, r, world)
+            shares.append(np.bincount(lut[c0:c0 + n], minlength=28) / n)
+        shares = np.asarray(shares)
+        assert np.abs(shares - shares.mean(axis=0)).max() < 0.03     # every rank sees the same class mix
+        runs = 1 + int((np.diff(lut) != 0).sum())
+        assert runs <= 28 * (w.ncol // 512 + world + 1)               # still long homogeneous runs inside a rank
 
 
 def _budget_from_oracle(w, c0, n, forcing):
