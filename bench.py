@@ -104,6 +104,18 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(nloc, nsteps, variant):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture, if it is of this exact launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            t = json.load(fh)
+        if t["columns"] == nloc and t["model_steps"] == nsteps and t["variant"] == variant:
+            return t["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def build_workload(args):
     w = synth.make_workload(args.workload, ncol=args.ncol, nsteps=args.model_steps)
     if not args.no_sort_columns:
@@ -128,14 +140,35 @@ def slice_workload(w, c0, n):
     return s
 
 
+def sample_workload(w, n):
+    """Every k-th column of the (class-sorted) workload: a representative sample with the same class mix."""
+    import copy
+    n = min(n, w.ncol)
+    idx = (np.arange(n, dtype=np.int64) * w.ncol) // n
+    s = copy.copy(w)
+    s.ncol = n
+    s.state = np.ascontiguousarray(w.state[:, idx])
+    s.static_f = np.ascontiguousarray(w.static_f[:, idx])
+    s.static_i = np.ascontiguousarray(w.static_i[idx])
+    s.sincos = np.ascontiguousarray(w.sincos[:, idx])
+    return s, idx
+
+
+def config_of(w, args, extra=None):
+    cfg = {"workload": w.name, "columns": w.ncol, "model_steps_per_step": w.nsteps, "dt_s": w.dt, "options": w.opts,
+           "column_order": "random (generator)" if args.no_sort_columns else "land-use type, latitude band; dealt round-robin to ranks"}
+    cfg.update(extra or {})
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline(w, sample_cols: int, fast: bool = True, repeats: int = 1) -> dict:
     """The reference's CPU path (C++ restatement of core/module_noahmp_func.f90; the Fortran cannot be
     compiled here) on all host cores, on the first `sample_cols` columns x all model steps."""
     from oracle.oracle import Oracle
-    n = min(sample_cols, w.ncol)
-    ws = slice_workload(w, 0, n)
-    forcing = synth.forcing_all(ws, col0=0)
+    ws, idx = sample_workload(w, sample_cols)
+    n = ws.ncol
+    forcing = synth.forcing_all(ws, cols=idx)
     o = Oracle(ParamTables.default(), w.opts, fast="fast" if fast else "parity")
     best = None
     for _ in range(repeats):
@@ -145,8 +178,8 @@ def cpu_baseline(w, sample_cols: int, fast: bool = True, repeats: int = 1) -> di
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return {"value": n * w.nsteps / best, "unit": UNIT, "cores": o.num_threads(), "kind": "port",
-            "sample": f"first {n} columns x {w.nsteps} model steps of {w.name} ({'-O3 AVX2+FMA' if fast else '-O2 no-FMA'} build, "
-                      f"OpenMP static, {best:.2f} s)"}
+            "sample": f"every {w.ncol // n}-th column ({n} columns) x {w.nsteps} model steps of {w.name} "
+                      f"({'-O3 AVX2+FMA' if fast else '-O2 no-FMA'} build of the C++ restatement, OpenMP static, {best:.2f} s)"}
 
 
 def run_reference(args):
@@ -154,10 +187,10 @@ def run_reference(args):
     if rank != 0:
         return
     w = build_workload(args)
-    n = min(args.cpu_sample_cols, w.ncol)
     from oracle.oracle import Oracle
-    ws = slice_workload(w, 0, n)
-    forcing = synth.forcing_all(ws, col0=0)
+    ws, idx = sample_workload(w, args.cpu_sample_cols)
+    n = ws.ncol
+    forcing = synth.forcing_all(ws, cols=idx)
     o = Oracle(ParamTables.default(), w.opts, fast="fast")
     times = []
     for it in range(args.warmup + args.steps):
@@ -172,11 +205,10 @@ def run_reference(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "columns": w.ncol, "model_steps_per_step": w.nsteps, "dt_s": w.dt,
-                       "options": w.opts, "sampled_columns": n},
+            "config": config_of(w, args, {"sampled_columns": n}),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": o.num_threads(), "kind": "port",
-                             "sample": f"first {n} columns x {w.nsteps} model steps per step (-O3 AVX2+FMA build of the C++ "
-                                       "restatement; the reference Fortran cannot be compiled in this image)"},
+                             "sample": f"every {w.ncol // n}-th column ({n} columns) x {w.nsteps} model steps per step (-O3 AVX2+FMA "
+                                       "build of the C++ restatement; the reference Fortran cannot be compiled in this image)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -324,14 +356,14 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": w.name, "columns": w.ncol, "columns_per_gpu": nloc, "model_steps_per_step": w.nsteps,
-                           "dt_s": w.dt, "options": w.opts, "variant": args.variant, "partition": f"block x{world}",
-                           "column_order": "random (generator)" if args.no_sort_columns else "land-use type, latitude band; dealt round-robin to ranks",
-                           "l2": "inputs larger than L2 (state+forcing per launch >> 126 MB); no flush needed"
-                                 if nloc * 4 * (2 * 44 + 9 * w.nsteps) > 2 * 126e6 else "inputs fit L2: traffic is L2-resident",
-                           "kernel": eng.kernel_info()},
+                "config": config_of(w, args, {
+                    "columns_per_gpu": nloc, "variant": args.variant, "partition": f"block x{world}",
+                    "l2": "inputs larger than L2 (state+forcing per launch >> 126 MB); no flush needed"
+                          if nloc * 4 * (2 * 44 + 9 * w.nsteps) > 2 * 126e6 else "inputs fit L2: traffic is L2-resident",
+                    "kernel": eng.kernel_info()}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "bytes_per_cell_step": B_ALG,
+                             "traffic": ncu_traffic(nloc, w.nsteps, args.variant), "traffic_unit": "bytes per launch (ncu dram__bytes_read+write)",
+                             "algorithmic_bytes_per_launch": B_ALG * nloc * w.nsteps, "peak_source": peak_src, "bytes_per_cell_step": B_ALG,
                              "kernel": "column_step_kernel", "kernel_ms": k_ms,
                              "note": "kernel is instruction-issue bound (see profiles/); fraction is reported against HBM as "
                                      "the contract asks"},

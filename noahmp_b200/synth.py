@@ -109,12 +109,13 @@ def step_scalars(w: Workload, step: int) -> dict:
             "t_seas": f32(w.synth.t_season * math.cos(2.0 * math.pi * (doy - 200.0) / w.yearlen))}
 
 
-def forcing_step(w: Workload, step: int, col0: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+def forcing_step(w: Workload, step: int, col0: int = 0, out: np.ndarray | None = None, cols=None) -> np.ndarray:
     """[NFORCING][ncol] fp32 forcing of one step.  ``col0`` = global index of this shard's first column
-    (multi-GPU shards hash GLOBAL column ids so the forcing does not depend on the rank count)."""
+    (multi-GPU shards hash GLOBAL column ids so the forcing does not depend on the rank count); ``cols`` =
+    explicit global column ids (for a strided sample of a larger workload)."""
     p = w.synth
     n = w.sincos.shape[1]
-    col = np.arange(col0, col0 + n, dtype=np.uint64).astype(np.uint32)
+    col = (np.arange(col0, col0 + n, dtype=np.uint64) if cols is None else np.asarray(cols, np.uint64)).astype(np.uint32)
     sc = step_scalars(w, step)
     sinlat, coslat = w.sincos[0], w.sincos[1]
     u = [uniform(p.seed, step, col, s) for s in range(12)]
@@ -155,10 +156,10 @@ def forcing_step(w: Workload, step: int, col0: int = 0, out: np.ndarray | None =
     return out
 
 
-def forcing_all(w: Workload, col0: int = 0) -> np.ndarray:
+def forcing_all(w: Workload, col0: int = 0, cols=None) -> np.ndarray:
     out = np.empty((w.nsteps, L.NFORCING, w.sincos.shape[1]), f32)
     for s in range(w.nsteps):
-        forcing_step(w, s, col0, out[s])
+        forcing_step(w, s, col0, out[s], cols=cols)
     return out
 
 
