@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--variant", default="fast", choices=["parity", "fast", "strict"])
     ap.add_argument("--no-sort-columns", action="store_true", help="keep the generator's random column order")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-variants", action="store_true", help="skip timing the parity/strict builds")
     ap.add_argument("--e2e-steps-per-launch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-cols", type=int, default=1_000_000)
@@ -286,6 +287,33 @@ def run_ours(args):
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     total_ms_max = float(t_max.item())
 
+    # ---- the other two builds of the same source on the same resident inputs (transparency: `value` is the fast
+    # build; the IEEE-arithmetic build and the fp64-libm verification build are reported next to it)
+    other = {}
+    if not args.no_other_variants:
+        for v in ("parity", "strict"):
+            if v == args.variant:
+                continue
+            eng_v = NoahMP(ParamTables.default(), w.opts, device=local, fast=v)
+            eng_v.set_stream(stream)
+            st_v = state0.clone()
+            rp0 = rp_of(w.julian0)
+            with torch.cuda.stream(stream):
+                eng_v.run(rp0, st_v, forcing, static_f, static_i)      # warm-up
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for k in range(2):
+                    eng_v.run(rp0, st_v, forcing, static_f, static_i)
+                e1.record(stream)
+            stream.synchronize()
+            tv = torch.tensor([e0.elapsed_time(e1) / 2.0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            other[v] = {"value": w.ncol * w.nsteps / (float(tv.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tv.item()),
+                        "kernel": eng_v.kernel_info()}
+            eng_v.close()
+            del st_v
+
     # ---- budget diagnostics of one extra pass + the only collective of the path (outside the timed region)
     with torch.cuda.stream(stream):
         chk = state0.clone()
@@ -367,7 +395,7 @@ def run_ours(args):
                              "kernel": "column_step_kernel", "kernel_ms": k_ms,
                              "note": "kernel is instruction-issue bound (see profiles/); fraction is reported against HBM as "
                                      "the contract asks"},
-                "e2e": e2e, "e2e_state_roundtrip": e2e_rt, "gpu_launches": int(launches), "clocks": clocks, "budget": bud}
+                "e2e": e2e, "e2e_state_roundtrip": e2e_rt, "other_variants": other, "gpu_launches": int(launches), "clocks": clocks, "budget": bud}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_sample_cols)
         elif not args.no_cpu_baseline:
