@@ -120,6 +120,17 @@ int noahmp_synth_forcing(noahmp_ctx* ctx, int64_t ncol, int64_t col0, uint32_t s
                          const float* coef17, const float* step_scalars4, const float* sincos_dev,
                          float* forcing_dev);
 
+/* ---- forcing preparation (the caller side of the path; the reference has the namelist
+ * fields `input_frequency` / `interval_seconds` but no code): time-interpolate two forcing records to the model
+ * step and compute COSZ.
+ *   rec0_dev, rec1_dev [8][ncol]  SFCTMP SFCPRS UU VV Q2 SOLDN LWDN PRCP at the two bracketing record times
+ *   weight                        (t - t0) / (t1 - t0) in [0,1]
+ *   geo_dev [4][ncol]             sin(lat) cos(lat) sin(lon) cos(lon)
+ *   scal4                         sin(decl), cos(decl), cos(H0), sin(H0)   (H0 = hour angle at longitude 0)
+ *   forcing_dev [NFORCING][ncol]  out: the 9 planes noahmp_run reads */
+int noahmp_prepare_forcing(noahmp_ctx* ctx, int64_t ncol, const float* rec0_dev, const float* rec1_dev, float weight,
+                           const float* geo_dev, const float scal4[4], float* forcing_dev);
+
 /* ---- introspection ------------------------------------------------------------------------------ */
 int noahmp_layout(int what); /* 0 NSTATE 1 NSTATE_CORE 2 NFORCING 3 NSTATIC_F 4 NDIAG 5 NGEN 6 NSOILP
                                 7 NCOLORP 8 NVEGF 9 NVEGI 10 sizeof(noahmp_run_params) 11 NBUDGET */

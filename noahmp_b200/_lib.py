@@ -15,7 +15,7 @@ class RunParams(C.Structure):  # struct noahmp_run_params
 
 # every symbol declared in include/noahmp_b200.h
 SYMBOLS = ["noahmp_init", "noahmp_finalize", "noahmp_set_stream", "noahmp_last_error", "noahmp_set_options",
-           "noahmp_set_tables", "noahmp_run", "noahmp_run_host", "noahmp_advance_host", "noahmp_synth_forcing", "noahmp_layout",
+           "noahmp_set_tables", "noahmp_run", "noahmp_run_host", "noahmp_advance_host", "noahmp_synth_forcing", "noahmp_prepare_forcing", "noahmp_layout",
            "noahmp_state_plane_name", "noahmp_forcing_plane_name", "noahmp_diag_plane_name", "noahmp_budget_name",
            "noahmp_launch_count", "noahmp_kernel_info"]
 
@@ -54,6 +54,7 @@ def load(fast=False) -> C.CDLL:
     lib.noahmp_advance_host.argtypes = [vp, C.POINTER(RunParams), C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     lib.noahmp_advance_host.restype = C.c_int64
     lib.noahmp_synth_forcing.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, C.c_int, fp, fp, vp, vp]
+    lib.noahmp_prepare_forcing.argtypes = [vp, C.c_int64, vp, vp, C.c_float, vp, fp, vp]
     lib.noahmp_layout.argtypes = [C.c_int]
     for f in ("noahmp_state_plane_name", "noahmp_forcing_plane_name", "noahmp_diag_plane_name", "noahmp_budget_name"):
         getattr(lib, f).argtypes = [C.c_int]

@@ -10,6 +10,7 @@
 
 #include "../../include/noahmp_b200.h"
 #include "column_step.cuh"
+#include "forcing_prep.cuh"
 
 using namespace nmp;
 
@@ -386,6 +387,28 @@ int noahmp_synth_forcing(noahmp_ctx* c, int64_t ncol, int64_t col0, uint32_t see
   const int block = 256;
   const int64_t grid = (ncol + block - 1) / block;
   synth_forcing_kernel<<<(unsigned)grid, block, 0, c->stream>>>(ncol, col0, p, sincos_dev, forcing_dev);
+  c->launches += 1;
+  CUDA_TRY(c, cudaGetLastError());
+  return 0;
+}
+
+int noahmp_prepare_forcing(noahmp_ctx* c, int64_t ncol, const float* rec0_dev, const float* rec1_dev, float weight,
+                           const float* geo_dev, const float scal4[4], float* forcing_dev) {
+  if (!c) return -1;
+  if (ncol <= 0) return 0;
+  if (!rec0_dev || !rec1_dev || !geo_dev || !scal4 || !forcing_dev) return fail(c, -1, "null argument");
+  if (!(weight >= 0.0f && weight <= 1.0f)) return fail(c, -5, "interpolation weight must be in [0,1]");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  PrepScalars p;
+  p.w = weight; p.sd = scal4[0]; p.cd = scal4[1]; p.ch0 = scal4[2]; p.sh0 = scal4[3];
+  const bool vec = (ncol % 4 == 0) && (((uintptr_t)rec0_dev | (uintptr_t)rec1_dev | (uintptr_t)geo_dev | (uintptr_t)forcing_dev) % 16 == 0);
+  const int block = 256;
+  const int64_t work = vec ? ncol / 4 : ncol;
+  int64_t grid = (work + block - 1) / block;
+  const int64_t cap = 148LL * 8 * 4;   // persistent-style: a few CTAs per SM, grid-stride loop
+  if (grid > cap) grid = cap;
+  if (vec) prepare_forcing_kernel<4><<<(unsigned)grid, block, 0, c->stream>>>(ncol, rec0_dev, rec1_dev, geo_dev, p, forcing_dev);
+  else prepare_forcing_kernel<1><<<(unsigned)grid, block, 0, c->stream>>>(ncol, rec0_dev, rec1_dev, geo_dev, p, forcing_dev);
   c->launches += 1;
   CUDA_TRY(c, cudaGetLastError());
   return 0;

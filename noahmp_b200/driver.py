@@ -1,26 +1,228 @@
-"""Time loop around the engine for the namelist-driven single-point case (BASELINE.json configs[0]).
+"""Offline driver around the engine: the time loop, forcing ingest, output and restart cadence the reference's
+namelist describes (offline/noahmp_config.py:77-102, run/case.nml) but nothing in the reference implements
+(SURVEY 8f ranks 1-3).  Host logic only; the column physics and the forcing preparation run on the GPU.
 
-What the reference leaves to a driver it never wrote: the step count from the namelist
-period, JULIAN / YEARLEN, cold-start state and forcing.  Forcing here is the synthetic generator of
-``synth.py``; a real ingest of ``input_directory`` files is a "next" item.
+Two modes:
+* file driven  -- ``initialization_file`` is an ``.npz`` of columns (see :func:`columns_from_init`) and
+  ``input_directory`` holds forcing records (``forcing.py``); outputs and restarts are written as ``.npz``.
+* synthetic    -- no initialization file: the single-point workload of ``synth.py`` over the namelist period
+  (BASELINE.json configs[0]).
 """
 from __future__ import annotations
 
-import calendar
+import datetime as dt
+import os
+from dataclasses import dataclass
 
 import numpy as np
 
+from . import forcing as F
 from . import layout as L, synth
 from .engine import NoahMP
 from .tables import ParamTables
 
+f32 = np.float32
+
+
+@dataclass
+class Columns:
+    state: np.ndarray      # [NSTATE][ncol]
+    static_f: np.ndarray   # [NSTATIC_F][ncol]
+    static_i: np.ndarray   # [ncol]
+    lat: np.ndarray        # radians
+    lon: np.ndarray        # radians
+
+    @property
+    def ncol(self) -> int:
+        return self.state.shape[1]
+
+
+# ------------------------------------------------------------------------------------------------
+def snow_layers_from_depth(snowh, sneqv, tsnow, zsoil=synth.ZSOIL):
+    """Initial snow layering from a bulk depth, following common upstream Noah-MP practice (the reference has no
+    initialisation code): < 0.025 m no layer; <= 0.05 one; <= 0.10 two halves; <= 0.25 0.05 + rest;
+    <= 0.45 0.05 + half + half of the rest; deeper 0.05 + 0.20 + rest.  Ice mass is spread by thickness.
+    Returns ISNOW [ncol] and DZ, SNICE [3][ncol] (layers -2..0), ZSNSO [7][ncol]."""
+    snowh = np.asarray(snowh, f32)
+    sneqv = np.asarray(sneqv, f32)
+    n = snowh.size
+    dz = np.zeros((3, n), f32)
+    isnow = np.zeros(n, np.int32)
+    a = (snowh >= 0.025) & (snowh <= 0.05)
+    isnow[a] = -1
+    dz[2, a] = snowh[a]
+    b = (snowh > 0.05) & (snowh <= 0.10)
+    isnow[b] = -2
+    dz[1, b] = snowh[b] / 2
+    dz[2, b] = snowh[b] / 2
+    c = (snowh > 0.10) & (snowh <= 0.25)
+    isnow[c] = -2
+    dz[1, c] = 0.05
+    dz[2, c] = snowh[c] - 0.05
+    d = (snowh > 0.25) & (snowh <= 0.45)
+    isnow[d] = -3
+    dz[0, d] = 0.05
+    dz[1, d] = 0.5 * (snowh[d] - 0.05)
+    dz[2, d] = 0.5 * (snowh[d] - 0.05)
+    e = snowh > 0.45
+    isnow[e] = -3
+    dz[0, e] = 0.05
+    dz[1, e] = 0.20
+    dz[2, e] = snowh[e] - 0.25
+    with np.errstate(divide="ignore", invalid="ignore"):
+        snice = np.where(dz > 0, dz * (sneqv / np.maximum(snowh, 1e-6)), 0.0).astype(f32)
+    zs = np.zeros((7, n), f32)
+    top = -np.cumsum(dz, axis=0)
+    for j in range(3):
+        zs[j] = np.where(dz[j] > 0, top[j], 0.0)
+    base = top[2]
+    for k in range(4):
+        zs[3 + k] = base + zsoil[k]
+    return isnow, dz, snice, zs
+
+
+def columns_from_init(path: str, tables: ParamTables) -> Columns:
+    """``.npz`` keys: lat, lon [deg]; lutyp, sltyp, slptyp, isc (ints); shdfac, tbot; tsk (skin T), stc[4], smc[4],
+    optional sh2o[4], snowh [m], sneqv [mm], canliq, zwt, wa."""
+    z = np.load(path)
+    n = z["lat"].size
+    st = synth._blank_state(n)
+    sl = z["sltyp"].astype(np.int64)
+    smcmax = np.asarray(tables.soil["SMCMAX"], f32)[sl - 1]
+    S = L.S
+    get = lambda k, default: (z[k].astype(f32) if k in z.files else np.full(n, default, f32))  # noqa: E731
+    snowh, sneqv = get("snowh", 0.0), get("sneqv", 0.0)
+    isnow, dz, snice, zs = snow_layers_from_depth(snowh, sneqv, None)
+    st[S["ISNOW"]] = isnow.view(f32)
+    multi = isnow < 0
+    st[S["SNOWH"]] = snowh
+    st[S["SNEQV"]] = sneqv
+    st[S["SNEQVO"]] = sneqv
+    tsk = z["tsk"].astype(f32)
+    for j in range(3):
+        st[L.snice(j - 2)] = snice[j]
+        st[L.stc(j - 2)] = np.where(dz[j] > 0, np.minimum(tsk, 273.15), 0.0)
+        st[L.zsnso(j - 2)] = zs[j]
+    for k in range(1, 5):
+        st[L.zsnso(k)] = zs[2 + k]
+        st[L.stc(k)] = z["stc"][k - 1]
+        st[L.smc(k)] = np.minimum(z["smc"][k - 1].astype(f32), smcmax)
+        st[L.soilwat(k)] = np.minimum(z["sh2o"][k - 1].astype(f32), st[L.smc(k)]) if "sh2o" in z.files else st[L.smc(k)]
+    del multi
+    st[S["TV"]] = tsk
+    st[S["TG"]] = tsk
+    st[S["TAH"]] = tsk
+    st[S["EAH"]] = get("eah", 2000.0)
+    st[S["ALBOLD"]] = 0.65
+    st[S["CANLIQ"]] = get("canliq", 0.0)
+    st[S["ZWT"]] = get("zwt", 2.5)
+    st[S["WA"]] = get("wa", 4900.0)
+    st[S["WT"]] = st[S["WA"]]
+    st[S["CM"]] = 0.1
+    st[S["CH"]] = 0.1
+    st[S["QSFC"]] = 0.005
+    st[S["LAI"]] = 2.0
+    st[S["SAI"]] = 0.5
+    lat, lon = np.deg2rad(z["lat"].astype(np.float64)), np.deg2rad(z["lon"].astype(np.float64))
+    sf = np.zeros((L.NSTATIC_F, n), f32)
+    sf[L.C["LAT"]] = lat
+    sf[L.C["SHDFAC"]] = get("shdfac", 0.7)
+    sf[L.C["TBOT"]] = get("tbot", 285.0)
+    sf[L.C["SHDMAX"]] = get("shdmax", 0.8)
+    ones = np.ones(n, np.int64)
+    si = L.pack_types(z["lutyp"].astype(np.int64), sl, z["slptyp"].astype(np.int64) if "slptyp" in z.files else ones,
+                      z["isc"].astype(np.int64) if "isc" in z.files else 4 * ones, ones, 0 * ones).astype(np.int32)
+    return Columns(st, sf, si, lat, lon)
+
+
+def write_restart(path: str, state: np.ndarray, when: dt.datetime, step: int) -> None:
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    np.savez(path, state=state, time=F.stamp(when), step=step, planes=np.asarray(L.STATE))
+
+
+def read_restart(path: str):
+    z = np.load(path)
+    if list(z["planes"]) != L.STATE:
+        raise ValueError(f"{path}: state plane list does not match this build")
+    return z["state"].astype(f32), dt.datetime.strptime(str(z["time"]), "%Y%m%d%H%M"), int(z["step"])
+
+
+# ------------------------------------------------------------------------------------------------
+def run_files(cfg, device: int = 0, variant="fast", max_steps_per_launch: int = 24) -> dict:
+    """The file-driven time loop.  Forcing valid at the start of each step; launches are cut at output and restart
+    boundaries and otherwise fuse up to ``max_steps_per_launch`` steps."""
+    import torch
+    tables = (ParamTables.from_tbl_dir(cfg.table_directory, cfg.soil_table_tag, cfg.veg_table_tag)
+              if getattr(cfg, "table_directory", None) else ParamTables.default(cfg.soil_table_tag, cfg.veg_table_tag))
+    cols = columns_from_init(cfg.initfile, tables)
+    t, step0 = cfg.begdatetime, 0
+    res_path = cfg.resfile if os.path.isabs(str(cfg.resfile)) else os.path.join(cfg.resdir, str(cfg.resfile))
+    if os.path.isfile(res_path):
+        cols.state, t, step0 = read_restart(res_path)
+    dtm = cfg.timestep
+    out_freq, res_freq = F.parse_frequency(cfg.outfreq), F.parse_frequency(cfg.resfreq)
+    dev = torch.device("cuda", device)
+    eng = NoahMP(tables, cfg.physics_options(), device=device, fast=variant)
+    ncol = cols.ncol
+    state = torch.from_numpy(cols.state).to(dev)
+    sf, si = torch.from_numpy(cols.static_f).to(dev), torch.from_numpy(cols.static_i).to(dev)
+    geo = torch.from_numpy(F.geo_planes(cols.lat, cols.lon)).to(dev)
+    diag = torch.zeros((L.NDIAG, ncol), dtype=torch.float32, device=dev)
+    budget = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
+    forcing = torch.empty((max_steps_per_launch, L.NFORCING, ncol), dtype=torch.float32, device=dev)
+    reader = F.RecordReader(cfg.indir, cfg.infreq, cfg.begdatetime, ncol, dev)
+    nsteps, written = step0, []
+    while t < cfg.enddatetime:
+        t_launch, g = t, 0
+        while g < max_steps_per_launch and t < cfg.enddatetime:
+            t0, t1, wgt = reader.bracket(t)
+            eng.prepare_forcing(reader.record(t0), reader.record(t1), wgt, geo, F.solar_scalars(t), forcing[g])
+            g += 1
+            t = t + dtm
+            if F.is_boundary(t, cfg.begdatetime, out_freq) or F.is_boundary(t, cfg.begdatetime, res_freq):
+                break
+        rp = eng.run_params(dtm.total_seconds(), synth.ZSOIL, F.julian_of(t_launch), F.yearlen_of(t_launch))
+        eng.run(rp, state, forcing[:g], sf, si, diag, budget)
+        nsteps += g
+        if F.is_boundary(t, cfg.begdatetime, out_freq):
+            os.makedirs(cfg.outdir, exist_ok=True)
+            p = os.path.join(cfg.outdir, F.stamp(t) + ".LDASOUT.npz")
+            np.savez(p, diag=diag.cpu().numpy(), planes=np.asarray(L.DIAG), time=F.stamp(t))
+            written.append(p)
+        if F.is_boundary(t, cfg.begdatetime, res_freq):
+            p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + ".npz")
+            write_restart(p, state.cpu().numpy(), t, nsteps)
+            written.append(p)
+    torch.cuda.synchronize()
+    out = _summary(state.cpu().numpy(), diag.cpu().numpy(), budget.cpu().numpy(), ncol, nsteps, dtm.total_seconds(),
+                   cfg.physics_options())
+    out["files_written"] = written
+    out["launches"] = eng.launch_count()
+    eng.close()
+    return out
+
+
+def _summary(st, dg, bd, ncol, nsteps, dt_s, opts) -> dict:
+    out = {"columns": ncol, "steps": nsteps, "dt_s": dt_s, "options": opts,
+           "flagged_column_launches": int(bd[L.B["NFLAGGED"]]), "max_abs_water_error_mm": float(bd[L.B["ERRWAT_MAXABS"]])}
+    for name in ("TV", "TG", "EAH", "SNEQV", "ZWT"):
+        out[name] = float(st[L.S[name]].mean())
+    for k in range(1, 5):
+        out[f"STC{k}"] = float(st[L.stc(k)].mean())
+        out[f"SMC{k}"] = float(st[L.smc(k)].mean())
+    for name in ("FSA", "FIRA", "FSH", "SSOIL", "TRAD"):
+        out[name] = float(dg[L.D[name]].mean())
+    return out
+
 
 def steps_of(cfg) -> int:
-    total = (cfg.enddatetime - cfg.begdatetime).total_seconds()
-    return int(total // cfg.timestep.total_seconds())
+    return int((cfg.enddatetime - cfg.begdatetime).total_seconds() // cfg.timestep.total_seconds())
 
 
-def run_case(cfg, ncol: int = 1, chunk: int = 96, device: int = 0, variant="parity") -> dict:
+def run_case(cfg, ncol: int = 1, chunk: int = 96, device: int = 0, variant="fast") -> dict:
+    """Entry used by run/main.py: file driven when the namelist's initialization file exists, else synthetic."""
+    if os.path.isfile(str(cfg.initfile)):
+        return run_files(cfg, device=device, variant=variant)
     import torch
     tables = (ParamTables.from_tbl_dir(cfg.table_directory, cfg.soil_table_tag, cfg.veg_table_tag)
               if getattr(cfg, "table_directory", None) else ParamTables.default(cfg.soil_table_tag, cfg.veg_table_tag))
@@ -28,9 +230,8 @@ def run_case(cfg, ncol: int = 1, chunk: int = 96, device: int = 0, variant="pari
     nsteps = steps_of(cfg)
     w = synth.make_workload("single", ncol=ncol, nsteps=nsteps, tables=tables, opts=opts)
     w.dt = float(cfg.timestep.total_seconds())
-    w.yearlen = 366 if calendar.isleap(cfg.begdatetime.year) else 365
-    w.julian0 = float(cfg.begdatetime.timetuple().tm_yday - 1) + (cfg.begdatetime.hour * 3600 + cfg.begdatetime.minute * 60
-                                                                + cfg.begdatetime.second) / 86400.0
+    w.yearlen = F.yearlen_of(cfg.begdatetime)
+    w.julian0 = F.julian_of(cfg.begdatetime)
     w.hour0 = cfg.begdatetime.hour + cfg.begdatetime.minute / 60.0
     eng = NoahMP(tables, opts, device=device, fast=variant)
     dev = torch.device("cuda", device)
@@ -42,20 +243,11 @@ def run_case(cfg, ncol: int = 1, chunk: int = 96, device: int = 0, variant="pari
     done = 0
     while done < nsteps:  # forcing is produced chunk by chunk, state stays on the device
         n = min(chunk, nsteps - done)
-        forcing = np.stack([synth.forcing_step(w, done + s) for s in range(n)])
+        fo = np.stack([synth.forcing_step(w, done + s) for s in range(n)])
         rp = eng.run_params(w.dt, synth.ZSOIL, w.julian0 + done * w.dt / 86400.0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
-        eng.run(rp, state, torch.from_numpy(forcing).to(dev), static_f, static_i, diag, budget)
+        eng.run(rp, state, torch.from_numpy(fo).to(dev), static_f, static_i, diag, budget)
         done += n
     torch.cuda.synchronize()
-    st, dg, bd = state.cpu().numpy(), diag.cpu().numpy(), budget.cpu().numpy()
-    out = {"columns": ncol, "steps": nsteps, "dt_s": w.dt, "options": opts,
-           "flagged_columns": int(bd[L.B["NFLAGGED"]]), "max_abs_water_error_mm": float(bd[L.B["ERRWAT_MAXABS"]])}
-    for name in ("TV", "TG", "EAH", "SNEQV", "ZWT"):
-        out[name] = float(st[L.S[name]].mean())
-    for k in range(1, 5):
-        out[f"STC{k}"] = float(st[L.stc(k)].mean())
-        out[f"SMC{k}"] = float(st[L.smc(k)].mean())
-    for name in ("FSA", "FIRA", "FSH", "SSOIL", "TRAD"):
-        out[name] = float(dg[L.D[name]].mean())
+    out = _summary(state.cpu().numpy(), diag.cpu().numpy(), budget.cpu().numpy(), ncol, nsteps, w.dt, opts)
     eng.close()
     return out

@@ -130,6 +130,14 @@ class NoahMP:
         self._check(self.lib.noahmp_synth_forcing(self.ctx, ncol, col0, seed, step, _fp(coef17), _fp(scalars4),
                                                   _dev_ptr(sincos), _dev_ptr(out)), "noahmp_synth_forcing")
 
+    def prepare_forcing(self, rec0, rec1, weight: float, geo, scal4: np.ndarray, out) -> None:
+        """``noahmp_prepare_forcing``: out[9,ncol] = time interpolation of two [8,ncol] records + COSZ (device tensors)."""
+        ncol = out.shape[1]
+        assert tuple(rec0.shape) == (8, ncol) and tuple(rec1.shape) == (8, ncol) and tuple(geo.shape) == (4, ncol)
+        self._check(self.lib.noahmp_prepare_forcing(self.ctx, ncol, _dev_ptr(rec0), _dev_ptr(rec1), float(weight), _dev_ptr(geo),
+                                                    _fp(np.ascontiguousarray(scal4, np.float32)), _dev_ptr(out)),
+                    "noahmp_prepare_forcing")
+
     # -- introspection -----------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.noahmp_launch_count(self.ctx))

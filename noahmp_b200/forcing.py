@@ -1,0 +1,118 @@
+"""Forcing ingest for the namelist-driven driver: record files at ``input_frequency``, time
+interpolation to ``interval_seconds`` and the cosine of the solar zenith angle -- none of which the reference
+implements (it only carries the config fields, offline/noahmp_config.py:81-86,98-102).
+
+Host side here = file I/O and the handful of per-step scalars; the per-column arithmetic runs on the GPU
+(``noahmp_prepare_forcing``).  Record files: ``<input_directory>/<YYYYMMDDHHMM>.npy``, float32 ``[8][ncol]`` in
+the order SFCTMP SFCPRS UU VV Q2 SOLDN LWDN PRCP (netCDF is not available in this image)."""
+from __future__ import annotations
+
+import calendar
+import datetime as dt
+import math
+import os
+import re
+
+import numpy as np
+
+RECORD_VARS = ["SFCTMP", "SFCPRS", "UU", "VV", "Q2", "SOLDN", "LWDN", "PRCP"]
+_UNITS = {"second": 1, "minute": 60, "hour": 3600, "day": 86400}
+
+
+def parse_frequency(text) -> tuple[int, str]:
+    """'1 hour' -> (3600, 'seconds'); '1 month' -> (1, 'months').  Accepts plural units and bare integers (seconds)."""
+    if isinstance(text, (int, float)):
+        return int(text), "seconds"
+    m = re.fullmatch(r"\s*(\d+)\s*([A-Za-z]+)\s*", str(text))
+    if not m:
+        raise ValueError(f"cannot parse frequency {text!r}")
+    n, unit = int(m.group(1)), m.group(2).lower().rstrip("s")
+    if unit == "month":
+        return n, "months"
+    if unit == "year":
+        return 12 * n, "months"
+    if unit not in _UNITS:
+        raise ValueError(f"unknown time unit in {text!r}")
+    return n * _UNITS[unit], "seconds"
+
+
+def advance(t: dt.datetime, freq: tuple[int, str]) -> dt.datetime:
+    n, kind = freq
+    if kind == "seconds":
+        return t + dt.timedelta(seconds=n)
+    month = t.month - 1 + n
+    year, month = t.year + month // 12, month % 12 + 1
+    return t.replace(year=year, month=month, day=min(t.day, calendar.monthrange(year, month)[1]))
+
+
+def is_boundary(t: dt.datetime, origin: dt.datetime, freq: tuple[int, str]) -> bool:
+    """True when ``t`` is ``origin`` plus a whole number of ``freq`` periods."""
+    n, kind = freq
+    if kind == "seconds":
+        return (t - origin).total_seconds() % n == 0
+    months = (t.year - origin.year) * 12 + (t.month - origin.month)
+    return months % n == 0 and (t.day, t.hour, t.minute, t.second) == (origin.day, origin.hour, origin.minute, origin.second)
+
+
+def stamp(t: dt.datetime) -> str:
+    return t.strftime("%Y%m%d%H%M")
+
+
+def julian_of(t: dt.datetime) -> float:
+    """JULIAN of noahmp_sflx (func:127): day of year as a float, 0.0 at 00:00 on 1 January."""
+    return (t.timetuple().tm_yday - 1) + (t.hour * 3600 + t.minute * 60 + t.second) / 86400.0
+
+
+def yearlen_of(t: dt.datetime) -> int:
+    return 366 if calendar.isleap(t.year) else 365
+
+
+def solar_scalars(t: dt.datetime) -> np.ndarray:
+    """sin(decl), cos(decl), cos(H0), sin(H0) for UTC time ``t``; H0 = hour angle at longitude 0.  Declination
+    by the cosine formula (23.44 deg amplitude, solstice on day 172); no equation of time."""
+    doy = julian_of(t) + 1.0
+    decl = math.radians(23.44) * math.cos(2.0 * math.pi * (doy - 172.0) / yearlen_of(t))
+    h0 = 2.0 * math.pi * ((t.hour + t.minute / 60.0 + t.second / 3600.0) - 12.0) / 24.0
+    return np.asarray([math.sin(decl), math.cos(decl), math.cos(h0), math.sin(h0)], np.float32)
+
+
+def geo_planes(lat_rad, lon_rad) -> np.ndarray:
+    """[4][ncol] fp32: sin(lat) cos(lat) sin(lon) cos(lon), evaluated in fp64 and rounded once."""
+    lat, lon = np.asarray(lat_rad, np.float64), np.asarray(lon_rad, np.float64)
+    return np.stack([np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)]).astype(np.float32)
+
+
+class RecordReader:
+    """Forcing records on disk, cached two at a time on the device."""
+
+    def __init__(self, directory: str, freq, origin: dt.datetime, ncol: int, device):
+        self.dir, self.freq, self.origin, self.ncol, self.device = directory, parse_frequency(freq), origin, ncol, device
+        if self.freq[1] != "seconds":
+            raise ValueError("input_frequency must be a fixed number of seconds")
+        self._cache: dict = {}
+
+    def path(self, t: dt.datetime) -> str:
+        return os.path.join(self.dir, stamp(t) + ".npy")
+
+    def bracket(self, t: dt.datetime):
+        """(t0, t1, weight) with t0 <= t < t1 on the record grid."""
+        n = self.freq[0]
+        k = int((t - self.origin).total_seconds() // n)
+        t0 = self.origin + dt.timedelta(seconds=k * n)
+        t1 = t0 + dt.timedelta(seconds=n)
+        return t0, t1, (t - t0).total_seconds() / n
+
+    def record(self, t: dt.datetime):
+        import torch
+        key = stamp(t)
+        if key not in self._cache:
+            p = self.path(t)
+            if not os.path.isfile(p):
+                raise FileNotFoundError(f"ERR: Unable to find forcing record {p}")
+            a = np.load(p)
+            if a.shape != (len(RECORD_VARS), self.ncol) or a.dtype != np.float32:
+                raise ValueError(f"{p}: expected float32 [{len(RECORD_VARS)}][{self.ncol}], got {a.dtype} {a.shape}")
+            if len(self._cache) >= 2:
+                self._cache.pop(sorted(self._cache)[0])
+            self._cache[key] = torch.from_numpy(a).to(self.device)
+        return self._cache[key]

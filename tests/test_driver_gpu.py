@@ -1,0 +1,102 @@
+"""GPU tests of the widened rows: forcing preparation kernel parity, file-driven run, restart continuity."""
+import datetime as dt
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from noahmp_b200 import forcing as F
+from noahmp_b200 import layout as L, synth
+from noahmp_b200.engine import NoahMP
+from oracle.forcing_prep import prepare_forcing
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("ncol", [1, 3, 4, 1000, 100_003, 262_144])
+def test_prepare_forcing_bit_exact(tables, ncol):
+    rng = np.random.default_rng(ncol)
+    a = rng.normal(280.0, 30.0, size=(8, ncol)).astype(np.float32)
+    b = rng.normal(280.0, 30.0, size=(8, ncol)).astype(np.float32)
+    geo = F.geo_planes(rng.uniform(-1.5, 1.5, ncol), rng.uniform(-3.1, 3.1, ncol))
+    eng = NoahMP(tables)
+    out = torch.empty((9, ncol), dtype=torch.float32, device=DEV)
+    for w, when in ((0.0, dt.datetime(2000, 1, 1)), (0.375, dt.datetime(2000, 7, 4, 17, 45)), (1.0, dt.datetime(2001, 12, 31, 23))):
+        s = F.solar_scalars(when)
+        eng.prepare_forcing(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV), w, torch.from_numpy(geo).to(DEV), s, out)
+        torch.cuda.synchronize()
+        ref = prepare_forcing(a, b, w, geo, s)
+        assert np.array_equal(out.cpu().numpy().view(np.int32), ref.view(np.int32)), (ncol, w)
+    eng.close()
+
+
+def _make_case(tmp_path, ncol=96, hours=7):
+    """Write an init file, hourly forcing records and a namelist; return the Config."""
+    import noahmp_config
+    w = synth.make_workload("global025", ncol=ncol, nsteps=1)
+    rng = np.random.default_rng(3)
+    lat = np.degrees(w.static_f[L.C["LAT"]].astype(np.float64))
+    init = dict(lat=lat, lon=rng.uniform(-120, 40, ncol), lutyp=w.static_i & 0xff, sltyp=(w.static_i >> 8) & 0xff,
+                slptyp=(w.static_i >> 16) & 0xff, isc=(w.static_i >> 24) & 0xf, shdfac=w.static_f[L.C["SHDFAC"]],
+                tbot=w.static_f[L.C["TBOT"]], tsk=w.state[L.S["TG"]], stc=np.stack([w.state[L.stc(k)] for k in range(1, 5)]),
+                smc=np.stack([w.state[L.smc(k)] for k in range(1, 5)]), snowh=np.where(lat > 55, 0.3, 0.0).astype(np.float32),
+                sneqv=np.where(lat > 55, 75.0, 0.0).astype(np.float32))
+    os.makedirs(tmp_path / "ldasin")
+    np.savez(tmp_path / "init.npz", **init)
+    t0 = dt.datetime(2000, 6, 30, 22)
+    for h in range(hours + 1):
+        t = t0 + dt.timedelta(hours=h)
+        rec = synth.forcing_step(w, h)[:8].copy()
+        np.save(tmp_path / "ldasin" / (F.stamp(t) + ".npy"), rec)
+    nml = f"""&NOAHMP_OFFLINE
+      static_parameter_file = 'none', initialization_file = '{tmp_path}/init.npz', restart_file = 'none.npz',
+      input_directory = '{tmp_path}/ldasin', input_frequency = '1 hour', output_directory = '{tmp_path}/out',
+      output_frequency = '3 hour', restart_directory = '{tmp_path}/restart', restart_frequency = '2 hour',
+      start_year = 2000, start_month = 6, start_day = 30, start_hour = 22, start_minute = 0, start_second = 0,
+      end_year = 2000, end_month = 7, end_day = 1, end_hour = {22 + hours - 24}, end_minute = 0, end_second = 0,
+      interval_seconds = 900,
+      opt_veg = 1, opt_run = 1, opt_btr = 1, opt_rad = 1, opt_tub = 1, opt_can = 1, opt_inf = 1, opt_tbot = 1, opt_snf = 1
+    /"""
+    (tmp_path / "case.nml").write_text(nml)
+    return noahmp_config.Config(str(tmp_path / "case.nml"))
+
+
+def test_file_driven_run_outputs_and_restart_continuity(tmp_path, tables):
+    from noahmp_b200.driver import read_restart, run_files
+    cfg = _make_case(tmp_path)
+    full = run_files(cfg, variant="parity")
+    assert full["steps"] == 28 and full["flagged_column_launches"] == 0 and full["columns"] == 96
+    names = sorted(os.path.basename(p) for p in full["files_written"])
+    assert names == ["200007010100.LDASOUT.npz", "200007010400.LDASOUT.npz", "RESTART.200007010000.npz",
+                     "RESTART.200007010200.npz", "RESTART.200007010400.npz"]
+    end_state, when, step = read_restart(str(tmp_path / "restart" / "RESTART.200007010400.npz"))
+    assert when == dt.datetime(2000, 7, 1, 4) and step == 24
+    out = np.load(tmp_path / "out" / "200007010400.LDASOUT.npz")
+    assert list(out["planes"]) == L.DIAG and np.isfinite(out["diag"][L.D["TRAD"]]).all()
+    # resume from the 02:00 restart: the remaining steps must reproduce the uninterrupted run bit for bit
+    cfg.resfile = str(tmp_path / "restart" / "RESTART.200007010200.npz")
+    resumed = run_files(cfg, variant="parity")
+    assert resumed["steps"] == 28
+    again, _, _ = read_restart(str(tmp_path / "restart" / "RESTART.200007010400.npz"))
+    assert np.array_equal(again.view(np.int32), end_state.view(np.int32))
+    # the snowy columns really carry layers and the forcing really varies in time
+    isn = end_state[L.S["ISNOW"]].view(np.int32)
+    assert (isn < 0).any() and (isn == 0).any()
+
+
+def test_main_entry_point_runs_the_synthetic_single_point(tmp_path):
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("noahmp_main", os.path.join(ROOT, "run", "main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)           # so the relative 'init.nc' of run/case.nml does not exist -> synthetic mode
+    try:
+        s = mod.main(os.path.join(ROOT, "run", "case.nml"), verbose=False)
+    finally:
+        os.chdir(cwd)
+    assert s["steps"] == 96 and s["columns"] == 1 and s["flagged_column_launches"] == 0
+    assert 250.0 < s["TG"] < 300.0 and s["max_abs_water_error_mm"] < 0.05
