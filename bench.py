@@ -141,6 +141,14 @@ def slice_workload(w, c0, n):
     return s
 
 
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which the CPU legs must not obey)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def sample_workload(w, n):
     """Every k-th column of the (class-sorted) workload: a representative sample with the same class mix."""
     import copy
@@ -175,10 +183,10 @@ def cpu_baseline(w, sample_cols: int, fast: bool = True, repeats: int = 1) -> di
     for _ in range(repeats):
         st = ws.state.copy()
         t0 = time.perf_counter()
-        o.run_workload(ws, forcing, state=st)
+        o.run_workload(ws, forcing, state=st, nthreads=host_threads())
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": n * w.nsteps / best, "unit": UNIT, "cores": o.num_threads(), "kind": "port",
+    return {"value": n * w.nsteps / best, "unit": UNIT, "cores": host_threads(), "kind": "port",
             "sample": f"every {w.ncol // n}-th column ({n} columns) x {w.nsteps} model steps of {w.name} "
                       f"({'-O3 AVX2+FMA' if fast else '-O2 no-FMA'} build of the C++ restatement, OpenMP static, {best:.2f} s)"}
 
@@ -197,7 +205,7 @@ def run_reference(args):
     for it in range(args.warmup + args.steps):
         st = ws.state.copy()
         t0 = time.perf_counter()
-        o.run_workload(ws, forcing, state=st)
+        o.run_workload(ws, forcing, state=st, nthreads=host_threads())
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -207,7 +215,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_of(w, args, {"sampled_columns": n}),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": o.num_threads(), "kind": "port",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port",
                              "sample": f"every {w.ncol // n}-th column ({n} columns) x {w.nsteps} model steps per step (-O3 AVX2+FMA "
                                        "build of the C++ restatement; the reference Fortran cannot be compiled in this image)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
