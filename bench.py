@@ -219,7 +219,7 @@ def run_reference(args):
                              "sample": f"every {w.ncol // n}-th column ({n} columns) x {w.nsteps} model steps per step (-O3 AVX2+FMA "
                                        "build of the C++ restatement; the reference Fortran cannot be compiled in this image)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -436,12 +436,30 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_sample_cols)
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else this process prints (NCCL banner, torchrun
+    notices, library chatter) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
