@@ -23,7 +23,8 @@ struct PrepScalars {
 __device__ __forceinline__ float lerp_rn(float a, float b, float w) { return __fadd_rn(a, __fmul_rn(w, __fsub_rn(b, a))); }
 __device__ __forceinline__ float cosz_rn(float sinlat, float coslat, float sinlon, float coslon, const PrepScalars& p) {
   const float ch = __fsub_rn(__fmul_rn(p.ch0, coslon), __fmul_rn(p.sh0, sinlon));
-  return __fadd_rn(__fmul_rn(sinlat, p.sd), __fmul_rn(__fmul_rn(coslat, p.cd), ch));
+  // clamped: fp32 rounding can overshoot 1 by an ulp and twostream takes acos(COSZ) (func:2315)
+  return fminf(fmaxf(__fadd_rn(__fmul_rn(sinlat, p.sd), __fmul_rn(__fmul_rn(coslat, p.cd), ch)), -1.0f), 1.0f);
 }
 
 // VEC = 4: ncol % 4 == 0 and 16-byte aligned planes; VEC = 1: anything

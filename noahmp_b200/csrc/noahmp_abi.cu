@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) synth_forcing_kernel(int64_t ncol, int64_
   const float s2 = MUL(sinlat, sinlat);
   const float tcore = ADD(ADD(p.t_mean, MUL(ADD(p.t_lat, p.t_seas), s2)), p.t_diur);
   const float T = ADD(tcore, MUL(p.t_noise, g1));
-  const float cosz = ADD(MUL(sinlat, p.sd), MUL(coslat, p.cdch));
+  const float cosz = fminf(fmaxf(ADD(MUL(sinlat, p.sd), MUL(coslat, p.cdch)), -1.0f), 1.0f);
   const float sw = MUL(p.sw_max, fmaxf(cosz, 0.0f));
   const float lw = ADD(ADD(p.lw_mean, MUL(p.lw_tcoef, SUB(T, p.t_mean))), MUL(p.lw_noise, g2));
   const float ps = ADD(p.p_mean, MUL(p.p_noise, SUB(MUL(2.0f, u[8]), 1.0f)));

@@ -126,6 +126,7 @@ def forcing_step(w: Workload, step: int, col0: int = 0, out: np.ndarray | None =
     tcore = (f32(p.t_mean) + (f32(p.t_lat) + sc["t_seas"]) * s2) + sc["t_diur"]
     T = tcore + f32(p.t_noise) * g1
     cosz = sinlat * sc["sd"] + coslat * sc["cdch"]
+    cosz = np.minimum(np.maximum(cosz, f32(-1.0)), f32(1.0))   # fp32 rounding can give 1.0000001: acos() in twostream needs <= 1
     sw = f32(p.sw_max) * np.maximum(cosz, f32(0.0))
     lw = (f32(p.lw_mean) + f32(p.lw_tcoef) * (T - f32(p.t_mean))) + f32(p.lw_noise) * g2
     ps = f32(p.p_mean) + f32(p.p_noise) * (two * u[8] - f32(1.0))

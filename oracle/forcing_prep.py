@@ -16,5 +16,5 @@ def prepare_forcing(rec0, rec1, weight, geo, scal4):
     out[:8] = rec0 + w * (rec1 - rec0)
     sinlat, coslat, sinlon, coslon = geo
     ch = ch0 * coslon - sh0 * sinlon
-    out[8] = sinlat * sd + (coslat * cd) * ch
+    out[8] = np.minimum(np.maximum(sinlat * sd + (coslat * cd) * ch, f32(-1.0)), f32(1.0))
     return out

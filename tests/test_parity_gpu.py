@@ -148,6 +148,46 @@ def test_noise_floor_is_the_physics(tables, oracle_libs):
         assert spread_gpu <= 5.0 * spread_cpu + 1e-6, (p, spread_gpu, spread_cpu)
 
 
+def test_one_year_run_stays_on_the_oracle(tables, oracle_libs):
+    """North-star target: state matching the reference path over a 1-year synthetic run (BASELINE config 3:
+    global 0.25 deg columns, mixed types, 8760 hourly steps; 1536-column subsample through the oracle, the
+    whole year fused into chunks of 24 steps on the GPU).  Strict build: bit-exact in >= 99% of the columns after
+    8760 steps (fp64 libm results can differ in ~2^-29 of ~1e10 calls; the physics then amplifies them).
+    Fast build: no closure flag all year, seasonal snowpack and soil state statistically on the oracle."""
+    ncol, nsteps = 1536, 8760
+    w = synth.make_workload("global025", ncol=ncol, nsteps=nsteps)
+    forcing = synth.forcing_all(w)
+    cs, _, cflag = cpu_run(tables, w, forcing, "strict")
+    assert cflag == 0
+    fo = torch.from_numpy(forcing).to(DEV)
+    sf, si = torch.from_numpy(w.static_f).to(DEV), torch.from_numpy(w.static_i).to(DEV)
+    res = {}
+    for variant in ("strict", "fast"):
+        eng = NoahMP(tables, w.opts, fast=variant)
+        st = torch.from_numpy(w.state.copy()).to(DEV)
+        bd = torch.zeros(L.NBUDGET, dtype=torch.float64, device=DEV)
+        for s0 in range(0, nsteps, 24):
+            rp = eng.run_params(w.dt, synth.ZSOIL, w.julian0 + s0 * w.dt / 86400.0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
+            eng.run(rp, st, fo[s0:s0 + 24], sf, si, None, bd)
+        torch.cuda.synchronize()
+        res[variant] = (st.cpu().numpy(), bd.cpu().numpy())
+        eng.close()
+    gs, gb = res["strict"]
+    assert gb[L.B["NFLAGGED"]] == 0
+    same_cols = (gs[:L.NSTATE_CORE].view(np.int32) == cs[:L.NSTATE_CORE].view(np.int32)).all(axis=0)
+    assert same_cols.mean() >= 0.99, f"only {same_cols.mean():.4f} of the columns are bit-identical after one year"
+    fs, fb = res["fast"]
+    assert fb[L.B["NFLAGGED"]] == 0 and fb[L.B["ERRWAT_MAXABS"]] < 0.1
+    assert (fs[L.S["ISNOW"]].view(np.int32) == cs[L.S["ISNOW"]].view(np.int32)).mean() >= 0.98
+    for p, tol in (("STC+4", 0.05), ("STC+1", 0.3), ("TG", 0.5)):
+        assert abs(float(fs[L.S[p]].mean()) - float(cs[L.S[p]].mean())) < tol, p
+        assert np.quantile(np.abs(fs[L.S[p]] - cs[L.S[p]]), 0.95) < 4 * tol, p
+    for p in ("SMC1", "SMC4", "WA", "ZWT"):
+        a, b = float(fs[L.S[p]].mean()), float(cs[L.S[p]].mean())
+        assert abs(a - b) <= 2e-3 * abs(b), p
+    assert abs(float(fs[L.S["SNEQV"]].mean()) - float(cs[L.S["SNEQV"]].mean())) <= 0.02 * max(float(cs[L.S["SNEQV"]].mean()), 1.0)
+
+
 # ---------------------------------------------------------------------------------------------- tier 3
 @pytest.mark.parametrize("variant", ["parity", "fast"])
 def test_full_size_conservation_and_determinism(tables, variant):
