@@ -136,7 +136,28 @@ __device__ __forceinline__ float pow5(float x) { float y = x * x; return y * y *
 __device__ __forceinline__ float m_powf(float x, float y) { return (float)pow((double)x, (double)y); }
 #else
 #define NMP_LIBM1(name, dname) __device__ __forceinline__ float m_##name(float x) { return name(x); }
+#ifdef NMP_ACCURATE_POW
+// under --use_fast_math `powf` becomes exp2(y*log2(x)) on the MUFU units (relative error ~|y log2 x| 2^-22);
+// libdevice's full-precision routine is still reachable by its internal name
+extern "C" __device__ float __nv_powf(float, float);
+__device__ __forceinline__ float m_powf(float x, float y) { return __nv_powf(x, y); }
+#else
 __device__ __forceinline__ float m_powf(float x, float y) { return powf(x, y); }
+#endif
+#endif
+// Correctly rounded quotient whatever -prec-div says.  The soil-moisture planes go volumetric -> mass -> volumetric
+// every step (func:4360/4423, 6527/6636); with the approximate reciprocal of the fast build x*d*rcp(d) is x(1+e) with the
+// SAME e each step (d = 1000 mm for layer 4 gives e = 4.75e-8), which compounds to 4e-4 of the deep soil moisture in a
+// year of hourly steps.  Those few conversions therefore divide exactly in every build.
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+// the soil hydraulic functions (func:6386-6455) raise SMC/SMCMAX to powers up to 2b+3 ~ 26 three to six times
+// per step; their error accumulates in the soil water, so they can be kept accurate on their own
+#if defined(NMP_ACCURATE_SOILPOW) && !defined(NMP_CR_LIBM)
+extern "C" __device__ float __nv_powf(float, float);
+__device__ __forceinline__ float m_soilpowf(float x, float y) { return __nv_powf(x, y); }
+#else
+__device__ __forceinline__ float m_soilpowf(float x, float y) { return m_powf(x, y); }
 #endif
 NMP_LIBM1(expf, exp)
 NMP_LIBM1(logf, log)

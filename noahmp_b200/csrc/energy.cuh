@@ -1322,8 +1322,8 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
           c.SNICE[IX3(k <= 0 ? k : 0)] = MICE;
           r.IMELT_snow[IX3(k <= 0 ? k : 0)] = IMELT;
         } else {
-          c.soilwat[IX4(k >= 1 ? k : 1)] = MLIQ / (1000.0f * DZSNSO[IX7(k)]);
-          c.SMC[IX4(k >= 1 ? k : 1)] = (MLIQ + MICE) / (1000.0f * DZSNSO[IX7(k)]);
+          c.soilwat[IX4(k >= 1 ? k : 1)] = div_rn(MLIQ, 1000.0f * DZSNSO[IX7(k)]);
+          c.SMC[IX4(k >= 1 ? k : 1)] = div_rn(MLIQ + MICE, 1000.0f * DZSNSO[IX7(k)]);
         }
       }
     });

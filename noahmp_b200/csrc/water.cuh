@@ -215,21 +215,21 @@ static_for<0, (3) - 1>([&](auto i_) { constexpr int i = decltype(i_)::value; DZS
 __device__ __forceinline__ void wdfcnd1(float smcmax, float bexp, float dwsat, float dksat, float SMC, float FCR,
                                         float& WDF, float& WCND) {
   const float FACTR = fmax2(0.01f, SMC / smcmax);
-  WDF = dwsat * m_powf(FACTR, bexp + 2.0f);
+  WDF = dwsat * m_soilpowf(FACTR, bexp + 2.0f);
   WDF = WDF * (1.0f - FCR);
-  WCND = dksat * m_powf(FACTR, 2.0f * bexp + 3.0f);
+  WCND = dksat * m_soilpowf(FACTR, 2.0f * bexp + 3.0f);
   WCND = WCND * (1.0f - FCR);
 }
 __device__ __forceinline__ void wdfcnd2(float smcmax, float bexp, float dwsat, float dksat, float SMC,
                                         float soilice, float& WDF, float& WCND) {
   const float FACTR = fmax2(0.01f, SMC / smcmax);
   const float EXPON = bexp + 2.0f;
-  WDF = dwsat * m_powf(FACTR, EXPON);
+  WDF = dwsat * m_soilpowf(FACTR, EXPON);
   if (soilice > 0.0f) {
-    const float VKWGT = 1.0f / (1.0f + m_powf(500.0f * soilice, 3.0f));
-    WDF = VKWGT * WDF + (1.0f - VKWGT) * dwsat * m_powf(0.2f / smcmax, EXPON);
+    const float VKWGT = 1.0f / (1.0f + m_soilpowf(500.0f * soilice, 3.0f));
+    WDF = VKWGT * WDF + (1.0f - VKWGT) * dwsat * m_soilpowf(0.2f / smcmax, EXPON);
   }
-  WCND = dksat * m_powf(FACTR, 2.0f * bexp + 3.0f);
+  WCND = dksat * m_soilpowf(FACTR, 2.0f * bexp + 3.0f);
 }
 
 struct WaterResult {
@@ -784,7 +784,7 @@ static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
       MLIQ[3] = MLIQ[3] + XS;
       runsub = runsub - XS / DT;
 static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- c.soilwat[IX4(k)] = MLIQ[IX4(k)] / (DZSNSO[IX7(k)] * 1000.0f);
+ c.soilwat[IX4(k)] = div_rn(MLIQ[IX4(k)], DZSNSO[IX7(k)] * 1000.0f);
       });
     }
     w.runsrf = runsrf;
@@ -861,7 +861,7 @@ static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
       c.WA = c.WA - XS;
       c.WT = c.WT - XS;
 static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- c.soilwat[IX4(k)] = MLIQ[IX4(k)] / DZMM[IX4(k)];
+ c.soilwat[IX4(k)] = div_rn(MLIQ[IX4(k)], DZMM[IX4(k)]);
       });
       w.runsub = QDIS;                                                                    // func:4790
     }

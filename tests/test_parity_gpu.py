@@ -153,7 +153,9 @@ def test_one_year_run_stays_on_the_oracle(tables, oracle_libs):
     global 0.25 deg columns, mixed types, 8760 hourly steps; 1536-column subsample through the oracle, the
     whole year fused into chunks of 24 steps on the GPU).  Strict build: bit-exact in >= 99% of the columns after
     8760 steps (fp64 libm results can differ in ~2^-29 of ~1e10 calls; the physics then amplifies them).
-    Fast build: no closure flag all year, seasonal snowpack and soil state statistically on the oracle."""
+    Fast build: no closure flag all year, and the 1e-4 tolerance of the north star held by >= 97 % of the columns in
+    every prognostic group with no systematic drift (the mass<->volumetric divisions are exact for that reason,
+    see div_rn in csrc/common.cuh)."""
     ncol, nsteps = 1536, 8760
     w = synth.make_workload("global025", ncol=ncol, nsteps=nsteps)
     forcing = synth.forcing_all(w)
@@ -179,13 +181,14 @@ def test_one_year_run_stays_on_the_oracle(tables, oracle_libs):
     fs, fb = res["fast"]
     assert fb[L.B["NFLAGGED"]] == 0 and fb[L.B["ERRWAT_MAXABS"]] < 0.1
     assert (fs[L.S["ISNOW"]].view(np.int32) == cs[L.S["ISNOW"]].view(np.int32)).mean() >= 0.98
-    for p, tol in (("STC+4", 0.05), ("STC+1", 0.3), ("TG", 0.5)):
-        assert abs(float(fs[L.S[p]].mean()) - float(cs[L.S[p]].mean())) < tol, p
-        assert np.quantile(np.abs(fs[L.S[p]] - cs[L.S[p]]), 0.95) < 4 * tol, p
-    for p in ("SMC1", "SMC4", "WA", "ZWT"):
-        a, b = float(fs[L.S[p]].mean()), float(cs[L.S[p]].mean())
-        assert abs(a - b) <= 2e-3 * abs(b), p
-    assert abs(float(fs[L.S["SNEQV"]].mean()) - float(cs[L.S["SNEQV"]].mean())) <= 0.02 * max(float(cs[L.S["SNEQV"]].mean()), 1.0)
+    # north-star tolerance: 1e-4 (relative) on the state after N steps.  The oracle itself, rebuilt with FMA contraction,
+    # keeps 98.5-99.5 % of the columns inside it after a year (tools/gpu_year_run.py); the fast build must do the same.
+    for p, frac in (("TG", 0.99), ("STC+1", 0.99), ("STC+4", 0.98), ("SMC1", 0.97), ("SMC4", 0.97), ("WA", 0.99), ("SNEQV", 0.99)):
+        a, b = fs[L.S[p]].astype(np.float64), cs[L.S[p]].astype(np.float64)
+        d = np.abs(a - b)
+        within = ((d <= 1e-4 * np.maximum(np.abs(a), np.abs(b))) | (d <= 1e-6)).mean()
+        assert within >= frac, f"{p}: only {within:.3f} of the columns within 1e-4 after one year"
+        assert abs(a.mean() - b.mean()) <= 2e-5 * max(abs(b.mean()), 1.0), f"{p}: systematic drift {a.mean() - b.mean():+.3e}"
 
 
 # ---------------------------------------------------------------------------------------------- tier 3
