@@ -110,7 +110,7 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.S
     const float JULIAN = (float)(rc.julian0 + (double)s * (double)DT / 86400.0);
     unsigned flags = 0;
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(0);
     // ---- atm, func:479-531 ------------------------------------------------------------------------
     const float THAIR = f.SFCTMP * m_powf(f.SFCPRS / f.SFCPRS, RAIR / CPAIR);
     const float QAIR = f.Q2;
@@ -205,12 +205,12 @@ static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
     const float QDEW = fabsf(fmin2(e.FGEV / e.LATHEAG, 0.0f));
     const float EDIR = QVAP - QDEW;
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(1);
     // ---- water ----------------------------------------------------------------------------------------
     WaterResult w;
     water<Opt>(opt, T, rc, c, f, e, QPRECC, QPRECL, elai, esai, fveg, QVAP, QDEW, FICEOLD, soilice, DZSNSO, w);
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(2);
     // ---- carbon, func:439-447 ---------------------------------------------------------------------------
     float GPP = 0.0f, NPP = 0.0f, NEE = 0.0f;
     if (OptTraits<Opt>::runtime) {

@@ -173,10 +173,15 @@ NMP_LIBM1(cosf, cos)
 // instruction caches, and ncu shows the warps starving on instruction fetch (stall_no_inst).  A CTA-wide
 // barrier at every phase boundary keeps all warps of the CTA inside the same few-KB code window, so a line
 // fetched for one warp is reused by the others.  Only placed where control flow is convergent.
+// Each site has a number (source order: 0-2 column_step, 3-14 energy, 15-18 water) so that a placement experiment
+// can drop single barriers with -DNMP_SYNC_MASK=0x... (bit n = site n on); the shipped builds keep them all.
+#ifndef NMP_SYNC_MASK
+#define NMP_SYNC_MASK 0xffffffffu
+#endif
 #ifdef NMP_PHASE_BARRIERS
-#define NMP_PHASE_SYNC() __syncthreads()
+#define NMP_PHASE_SYNC_AT(n) do { if ((NMP_SYNC_MASK >> (n)) & 1u) __syncthreads(); } while (0)
 #else
-#define NMP_PHASE_SYNC() ((void)0)
+#define NMP_PHASE_SYNC_AT(n) ((void)0)
 #endif
 // Loops whose trip count depends on the data (canopy Newton loop, stomata bisection, soil sub-steps) can be
 // run CTA-uniform (-DNMP_UNIFORM_LOOPS: every thread executes the loop control, one barrier per pass).

@@ -66,6 +66,14 @@ __device__ __forceinline__ void esat(float T, float& ESW, float& ESI, float& DES
          T * (3.005693132E-07f + T * (2.158542548E-09f + T * 7.131097725E-12f))))));
 }
 __device__ __forceinline__ float tdc(float T) { return fmin2(50.0f, fmax2(-50.0f, (T - TFRZ))); }  // func:2688
+// Every caller keeps the over-water pair for T > 0 and the over-ice pair otherwise (func:2789-2797, 2889-2897, 3176-3184,
+// 2712-2718, 3225-3231).  Evaluating only the pair a warp needs (vote + branch) was measured and is SLOWER (2.51e9 ->
+// 2.31e9 cell-steps/s): the 24 independent FMAs are cheap filler for the issue slots, the vote and branches are not.
+__device__ __forceinline__ void esat_sel(float T, float& ES, float& DES) {
+  float ESW, ESI, DESW, DESI;
+  esat(T, ESW, ESI, DESW, DESI);
+  if (T > 0.0f) { ES = ESW; DES = DESW; } else { ES = ESI; DES = DESI; }
+}
 
 // ---- func:1500-1595  Johansen / Peters-Lidard soil conductivity ------------------------------------
 __device__ __forceinline__ float tdfcnd(float smcmax, float quartz, float SMC, float soilwat) {
@@ -444,9 +452,7 @@ struct Loop1 {
     const float TMPRB = CWPC * 50.0f / (1.0f - m_expf(-CWPC / 2.0f));
     RB = TMPRB * rbfac;
     const float Tc = tdc(TV);                                                             // func:2787-2795
-    float ESATW, ESATI, DSATW, DSATI;
-    esat(Tc, ESATW, ESATI, DSATW, DSATI);
-    if (Tc > 0.0f) { ESTV = ESATW; DESTV = DSATW; } else { ESTV = ESATI; DESTV = DSATI; }
+    esat_sel(Tc, ESTV, DESTV);
   }
 
   __device__ __forceinline__ void second(int iter) {
@@ -555,7 +561,7 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
   if (ZPDG >= ZLVL) ZLVL = ZPDG + rc.zref;
   const float CWP = VG[V_CWPVT];                                                          // func:1084
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(3);
   // ---- thermoprop, func:1341-1445 (+ csnow 1448-1497, tdfcnd) -----------------------------------
   float DF[7], HCPCT[7], FACT[7];
 static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
@@ -571,7 +577,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     }
   });
 static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                      // func:1398-1403
-    NMP_PHASE_SYNC();
+    NMP_PHASE_SYNC_AT(4);
     const float soilice = c.SMC[IX4(k)] - c.soilwat[IX4(k)];
     HCPCT[IX7(k)] = c.soilwat[IX4(k)] * CWAT + (1.0f - SMCMAX) * T.gen[G_CSOIL] + (SMCMAX - c.SMC[IX4(k)]) * CPAIR +
                     soilice * CICE;
@@ -588,7 +594,7 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;     
   if (ISNOW == 0) DF[IX7(1)] = (DF[IX7(1)] * DZSNSO[IX7(1)] + 0.35f * c.snowh) / (c.snowh + DZSNSO[IX7(1)]);  // func:1440-1444
   else DF[IX7(1)] = (DF[IX7(1)] * DZSNSO[IX7(1)] + DF[IX7(0)] * DZSNSO[IX7(0)]) / (DZSNSO[IX7(0)] + DZSNSO[IX7(1)]);
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(5);
   // ---- radiation, func:1598-1714: albedo (1717-1887) + surrad (1890-2005) ----------------------
   float FSUN = 0.0f, BGAP = 0.0f, WGAP = 0.0f;
   float ALBGRD[2] = {0.0f, 0.0f}, ALBGRI[2] = {0.0f, 0.0f}, ALBD[2] = {0.0f, 0.0f}, ALBI[2] = {0.0f, 0.0f};
@@ -658,7 +664,7 @@ static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
   }
 #pragma unroll 1
   for (int call = 0; call < 4; ++call) {
-    NMP_PHASE_SYNC();
+    NMP_PHASE_SYNC_AT(6);
     if (day) {
       const int ib = call >> 1, ic = call & 1;
       TwoStreamOut o;
@@ -715,7 +721,7 @@ static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
   dg.put(D_WGAP, WGAP);
   dg.put(D_FSNO, FSNO);
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(7);
   // ---- emissivities, soil-moisture stress, surface resistance: func:1106-1189 -------------------
   const float EMV = 1.0f - m_expf(-(elai + esai) / 1.0f);
   float EMG;
@@ -785,7 +791,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   float CHV2 = 0.0f, TGV = 0.0f, CMV = 0.0f, RSSUN = 0.0f, RSSHA = 0.0f;
   float QSFC = c.QSFC;
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(8);
   // ---- vege_flux, func:2465-2964 ----------------------------------------------------------------
   // The three Newton loops run as CTA-uniform loops (NMP_ANY = __syncthreads_or when phase barriers are
   // on): every thread executes the loop control, the body is predicated on the lane still iterating.  Per
@@ -796,7 +802,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   mo.MOZ = 0.0f; mo.FM = 0.0f; mo.FH = 0.0f; mo.FM2 = 0.0f; mo.FH2 = 0.0f; mo.FV = 0.1f; mo.CM = c.CM; mo.CH = c.CH;
   mo.CH2 = 0.0f; mo.MOZSGN = 0;
   float RAHG = 0.0f, RAWG = 0.0f;
-  float ESATW, ESATI, DSATW, DSATI, ESTG = 0.0f, CAH = 0.0f, CVH = 0.0f;
+  float ESTG = 0.0f, CAH = 0.0f, CVH = 0.0f;
   float HCAN = HTOP, AIR = 0.0f, CIR = 0.0f;
   float CSH = 0.0f, CEV = 0.0f, CGH = 0.0f;
   const float Z0H = Z0M;                                                                  // func:2746-2752
@@ -823,8 +829,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     L.LAISUNE = fmin2(6.0f, LAISUN / fveg);
     L.LAISHAE = fmin2(6.0f, LAISHA / fveg);
     const float Tc = tdc(TGV);                                                            // func:2710-2716
-    esat(Tc, ESATW, ESATI, DSATW, DSATI);
-    ESTG = (Tc > 0.0f) ? ESATW : ESATI;
+    { float unused; esat_sel(Tc, ESTG, unused); }
     L.ESTG = ESTG;
     L.QSFC = 0.622f * EAIR / (PSFC - 0.378f * EAIR);                                      // func:2720
     const float UC = UR * m_logf(HCAN / Z0M) / m_logf(ZLVL / Z0M);                        // func:2725
@@ -838,7 +843,8 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   }
   // ---- loop1, func:2744-2877.  The exit test cannot fire before the end of pass 6 (LITER is set at
   // pass >= 5 and acts one pass later), so passes 1..6 run for every canopy column; the data-dependent tail
-  // (passes 7..20, ~17% of the columns) is what makes warps diverge.
+  // (passes 7..20; on the CONUS workload half of the column-steps need at least one, 0.4% all fourteen) is what
+  // makes warps diverge: 22.8% of the kernel's warp-instructions at 12.3 lanes active (profiles/r01_e).
 #pragma unroll 1
   for (int iter = 1; iter <= 6; ++iter) {
     if (L.running) L.first(opt, iter);
@@ -871,9 +877,10 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     }
     if (L.running) L.second(iter);
   }
+  // ---- loop1 tail, passes 7..20 (only the lanes still iterating) --------------------------------------
 #ifdef NMP_COMPACT_LOOP1
   {
-    // ---- tail compaction: columns that still iterate after pass 6 are packed into the first warps of the
+    // optional tail compaction: columns that still iterate after pass 6 are packed into the first warps of the
     // CTA through shared memory, so the tail runs on full warps instead of a few lanes per warp.
     __shared__ float xch[LOOP1_WORDS][LOOP1_CAP];
     __shared__ int xcnt;
@@ -958,7 +965,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     mo = L.mo; TAH = L.TAH; EAH = L.EAH; TV = L.TV; RAHG = L.RAHG; RAWG = L.RAHG; CAH = L.CAH; CVH = L.CVH;
     IRC = L.IRC; SHC = L.SHC; EVC = L.EVC; TR = L.TR; QSFC = L.QSFC; AIR = L.AIR; CIR = L.CIR;
   }
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(9);
   // under-canopy ground temperature, loop2, func:2881-2914
   if (veg_tile) {
     AIR = -EMG * (1.0f - EMV) * f.LWDN - EMG * EMV * SB * pow4(TV);
@@ -969,9 +976,8 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
 #pragma unroll 1
     for (int iter = 1; iter <= 5; ++iter) {
       const float Tc = tdc(TGV);
-      esat(Tc, ESATW, ESATI, DSATW, DSATI);
       float DESTG;
-      if (Tc > 0.0f) { ESTG = ESATW; DESTG = DSATW; } else { ESTG = ESATI; DESTG = DSATI; }
+      esat_sel(Tc, ESTG, DESTG);
       IRG = CIR * pow4(TGV) + AIR;
       SHG = CSH * (TGV - TAH);
       EVG = CEV * (ESTG * RHSUR - EAH);
@@ -1015,7 +1021,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     c.TV = TV;
   }
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(10);
   // ---- bare_flux, func:2967-3257 ----------------------------------------------------------------
   float TGB = c.TG, CMB = c.CM, CHB = c.CH, TAUXB, TAUYB, IRB = 0.0f, SHB = 0.0f, EVB = 0.0f, GHB = 0.0f, T2MB, Q2B, CHB2;
   {
@@ -1032,7 +1038,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     float ESTGb = 0.0f, CSHb = 0.0f, CEVb = 0.0f, EHB = 0.0f;
 #pragma unroll 1
     for (int iter = 1; iter <= 5; ++iter) {                                               // loop3, func:3134-3222
-      NMP_PHASE_SYNC();
+      NMP_PHASE_SYNC_AT(11);
       if (opt.sfc == 1) {
         sfcdif1(iter, f.SFCTMP, RHOAIR, Hb, QAIR, ZLVL, ZPDb, Z0Hb, UR, TMPCMb, TMPCHb, TMPCM2b, TMPCH2b, mb);
       }
@@ -1049,9 +1055,8 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       const float RAWB = RAHB;
       EHB = 1.0f / RAHB;
       float Tc = tdc(TGB);                                                                // func:3176-3184
-      esat(Tc, ESATW, ESATI, DSATW, DSATI);
       float DESTG;
-      if (Tc > 0.0f) { ESTGb = ESATW; DESTG = DSATW; } else { ESTGb = ESATI; DESTG = DSATI; }
+      esat_sel(Tc, ESTGb, DESTG);
       CSHb = RHOAIR * CPAIR / RAHB;                                                       // func:3186-3187
       CEVb = RHOAIR * CPAIR / GAMMAG / (RSURF + RAWB);
       IRB = CIRb * pow4(TGB) - EMG * f.LWDN;                                              // func:3191-3194
@@ -1068,8 +1073,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       TGB = TGB + DTG;
       Hb = CSHb * (TGB - f.SFCTMP);                                                       // func:3209
       Tc = tdc(TGB);                                                                      // func:3211-3218
-      esat(Tc, ESATW, ESATI, DSATW, DSATI);
-      ESTGb = (Tc > 0.0f) ? ESATW : ESATI;
+      { float unused; esat_sel(Tc, ESTGb, unused); }
       QSFC = 0.622f * (ESTGb * RHSUR) / (PSFC - 0.378f * (ESTGb * RHSUR));
     }
     if (opt.stc == 1) {                                                                   // func:3225-3233
@@ -1097,7 +1101,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   }
   (void)TAUXV; (void)TAUYV; (void)TAUXB; (void)TAUYB;   // wind stress is computed by the reference but never returned
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(12);
   // ---- tile aggregation, func:1246-1308 ---------------------------------------------------------
   float FIRA, FSH, FGEV, SSOIL, FCEV, FCTR, TS;
   if (VEG && fveg > 0.0f) {
@@ -1133,7 +1137,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   r.CH_out = c.CH;
   r.Q2B = Q2B;
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(13);
   // ---- tsnosoi: hrt + hstep + rosr12, func:3987-4288 ---------------------------------------------
   {
     const float ZBOTSNO = T.gen[G_ZBOT] - c.snowh;                                        // func:4039
@@ -1214,7 +1218,7 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     }
   }
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(14);
   // ---- phasechange, func:4291-4491 (layers are independent: one pass, per-layer scalars) ---------
   {
     float QMELT = 0.0f, PONDING = 0.0f;

@@ -76,6 +76,10 @@ int cuda_fail(noahmp_ctx* c, cudaError_t e, const char* where) {
 typedef void (*StepKernel)(const StepArgs);
 
 StepKernel pick_kernel(bool is_default, bool diag, bool budget) {
+#ifdef NMP_EXPERIMENT_ONE_KERNEL   // tuning builds only (tools/tune_builds.sh): compile just the benchmarked variant
+  (void)is_default; (void)diag; (void)budget;
+  return column_step_kernel<OptDefault, false, false, false>;
+#else
   if (is_default) {
     if (diag) return column_step_kernel<OptDefault, false, true, true>;
     if (budget) return column_step_kernel<OptDefault, false, false, true>;
@@ -84,6 +88,7 @@ StepKernel pick_kernel(bool is_default, bool diag, bool budget) {
   if (diag) return column_step_kernel<OptRuntime, true, true, true>;
   if (budget) return column_step_kernel<OptRuntime, true, false, true>;
   return column_step_kernel<OptRuntime, true, false, false>;
+#endif
 }
 
 // ---- synthetic forcing: integer hash + explicit round-to-nearest fp32 ops (no FMA contraction), so it

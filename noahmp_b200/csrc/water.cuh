@@ -341,7 +341,7 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
     c.QSNOW = QSNOW;
   }
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(15);
   // ---- ground evaporation / dew split between snow and soil, func:4725-4735 ----------------------
   float QSNSUB = 0.0f;
   if (c.sneqv > 0.0f) QSNSUB = fmin2(QVAP, c.sneqv / DT);
@@ -534,7 +534,7 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   }
   w.QSNBOT = QSNBOT; w.PONDING1 = PONDING1; w.PONDING2 = PONDING2;
 
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(16);
   if (e.frozen_ground) {                                                                  // func:4744-4752
     soilice[0] = soilice[0] + (QSDEW - QSEVA) * DT / (DZSNSO[IX7(1)] * 1000.0f);
     QSDEW = 0.0f;
@@ -563,7 +563,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   float SICEMAX = 0.0f, FCRMAX = 0.0f;
   int niter = 1;
   float dtfine = DT, QDRAIN_SAVE = 0.0f;
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(17);
   if (soil_col) {
 static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                    // func:5893-5897
       const float epore = fmax2(1.0E-4f, (SMCMAX - soilice[IX4(k)]));
@@ -754,7 +754,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       QDRAIN_SAVE = QDRAIN_SAVE + QDRAIN;
     }
   }
-  NMP_PHASE_SYNC();
+  NMP_PHASE_SYNC_AT(18);
   if (soil_col) {
     QDRAIN = QDRAIN_SAVE / (float)niter;                                                  // func:5998-6001
     runsrf = runsrf * 1000.0f + RSAT * 1000.0f / DT;
