@@ -12,6 +12,8 @@ test_noise_floor_is_the_physics):
     columns (tolerance written per test), closure residuals within the reference's own 0.01 W/m2 asserts.
  3. size-independent properties at full scale: conservation flags, determinism, host-entry == device-entry.
 """
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -226,6 +228,42 @@ def test_full_size_conservation_and_determinism(tables, variant):
     multi = isn < 0
     assert np.allclose(tot[multi], s1[L.S["SNEQV"]][multi], rtol=1e-5)          # func:5147-5152
     assert (s1[L.zsnso(4)][multi] < s1[L.zsnso(1)][multi]).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("name,nsteps,nsample", [("snow1m", 720, 2048), ("global025", 8760, 512)])
+def test_full_size_full_length_sample_is_bit_exact(tables, oracle_libs, name, nsteps, nsample):
+    """BASELINE configs[4] (1e6 columns x 720 steps) and configs[2] (280 000 columns x 8760 steps) at FULL size and FULL
+    length on the strict build, forcing generated on the device 24 steps at a time; every (ncol/nsample)-th column is
+    also carried through the strict oracle and must come out bit for bit (parity on a subsample through the
+    oracle, the full set on the GPU).  No closure flag anywhere in the full set."""
+    w = synth.make_workload(name, nsteps=nsteps)
+    idx = (np.arange(nsample, dtype=np.int64) * w.ncol) // nsample
+    ws = copy.copy(w)
+    ws.ncol, ws.state, ws.static_f = nsample, np.ascontiguousarray(w.state[:, idx]), np.ascontiguousarray(w.static_f[:, idx])
+    ws.static_i, ws.sincos = np.ascontiguousarray(w.static_i[idx]), np.ascontiguousarray(w.sincos[:, idx])
+    cs = ws.state.copy()
+    assert Oracle(tables, w.opts, fast="strict").run_workload(ws, synth.forcing_all(ws, cols=idx), state=cs) == 0
+    eng = NoahMP(tables, w.opts, fast="strict")
+    st = torch.from_numpy(w.state.copy()).to(DEV)
+    sf, si = torch.from_numpy(w.static_f).to(DEV), torch.from_numpy(w.static_i).to(DEV)
+    sincos = torch.from_numpy(w.sincos).to(DEV)
+    fo = torch.empty((24, L.NFORCING, w.ncol), dtype=torch.float32, device=DEV)
+    bd = torch.zeros(L.NBUDGET, dtype=torch.float64, device=DEV)
+    coef = synth.synth_params_array(w.synth)
+    for s0 in range(0, nsteps, 24):
+        for s in range(24):
+            sc = synth.step_scalars(w, s0 + s)
+            eng.synth_forcing(w.ncol, 0, w.synth.seed, s0 + s, coef, np.asarray([sc["sd"], sc["cdch"], sc["t_diur"], sc["t_seas"]], f32),
+                              sincos, fo[s])
+        rp = eng.run_params(w.dt, synth.ZSOIL, w.julian0 + s0 * w.dt / 86400.0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
+        eng.run(rp, st, fo, sf, si, None, bd)
+    torch.cuda.synchronize()
+    b = bd.cpu().numpy()
+    assert b[L.B["NFLAGGED"]] == 0 and b[L.B["ERRWAT_MAXABS"]] < 0.1
+    gs = st[:, torch.from_numpy(idx).to(DEV)].cpu().numpy()
+    same = (gs[:L.NSTATE_CORE].view(np.int32) == cs[:L.NSTATE_CORE].view(np.int32)).all(axis=0)
+    assert same.mean() >= 0.99, f"{name}: only {same.mean():.4f} of the sampled columns bit-identical after {nsteps} steps"
     eng.close()
 
 
