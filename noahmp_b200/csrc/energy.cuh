@@ -497,21 +497,74 @@ struct Loop1 {
     else if (iter >= 5 && fabsf(DTV) <= 0.01f) LITER = 1;
   }
 };
-// field lists for the shared-memory hand-off (member-wise, so the struct itself stays in registers)
-#define NMP_LOOP1_FLOATS(X)                                                                                          \
+// Field lists for the shared-memory hand-off of a column's loop state (member-wise, so the struct itself stays in
+// registers): what a pass only reads, what it carries from pass to pass, and what the caller reads after the last pass.
+// Left out on purpose, so that the compiler can still drop them as dead code: mo.FM2 / mo.CH2 (the 2-m momentum
+// functions, computed by func:3449-3498 and read by nobody), the first()->second() temporaries RAHC RB ESTV DESTV, and
+// QSFC (a function of the final EAH, recomputed by the receiver).  THAIR CZIL WSTAR travel only for opt_sfc = 2.
+#define NMP_LOOP1_CONST(X)                                                                                           \
   X(SFCTMP) X(RHOAIR) X(QAIR) X(ZLVL) X(ZPD) X(Z0M) X(UR) X(TMPCM) X(TMPCH) X(TMPCM2) X(TMPCH2) X(Z0MG) X(CWP) X(VAIE)  \
   X(HCAN) X(rbfac) X(TGV) X(FWET) X(LAISUNE) X(LAISHAE) X(RSSUN) X(RSSHA) X(RSURF) X(EAIR) X(ESTG) X(GAMMAV) X(fveg)   \
-  X(AIR) X(CIR) X(SAV) X(SFCPRS) X(evcap_liq) X(evcap_ice) X(THAIR) X(CZIL) X(mo.MOZ) X(mo.FM) X(mo.FH) X(mo.FM2)       \
-  X(mo.FH2) X(mo.FV) X(mo.CM) X(mo.CH) X(mo.CH2) X(WSTAR) X(H) X(HG) X(FHG) X(TAH) X(EAH) X(TV) X(RAHC) X(RAHG) X(RB)   \
-  X(ESTV) X(DESTV) X(CAH) X(CVH) X(IRC) X(SHC) X(EVC) X(TR) X(QSFC)
-#define NMP_LOOP1_INTS(X) X(mo.MOZSGN) X(LITER) X(iter_done) X(running)
+  X(AIR) X(CIR) X(SAV) X(SFCPRS) X(evcap_liq) X(evcap_ice)
+#define NMP_LOOP1_SFC2(X) X(THAIR) X(CZIL) X(WSTAR)
+#define NMP_LOOP1_VARF(X)                                                                                            \
+  X(mo.MOZ) X(mo.FM) X(mo.FH) X(mo.FH2) X(mo.FV) X(mo.CM) X(mo.CH) X(H) X(HG) X(FHG) X(TAH) X(EAH) X(TV)
+#define NMP_LOOP1_VARI(X) X(mo.MOZSGN) X(LITER) X(iter_done) X(running)
+#define NMP_LOOP1_OUT(X) X(RAHG) X(CAH) X(CVH) X(IRC) X(SHC) X(EVC) X(TR)
 #define NMP_COUNT(f) +1
-constexpr int LOOP1_WORDS = 0 NMP_LOOP1_FLOATS(NMP_COUNT) NMP_LOOP1_INTS(NMP_COUNT);
-static_assert(LOOP1_WORDS * 4 == sizeof(Loop1), "hand-off field lists must cover every member of Loop1");
-// Slots of the CTA-shared hand-off buffer: about 17% of the vegetated columns need more than the 6 mandatory
-// passes, so 3/8 of the CTA is ample; overflow lanes simply keep iterating in place.
+constexpr int LOOP1_NCONST = 0 NMP_LOOP1_CONST(NMP_COUNT);
+constexpr int LOOP1_NVAR = 0 NMP_LOOP1_VARF(NMP_COUNT) NMP_LOOP1_VARI(NMP_COUNT);
+constexpr int LOOP1_NOUT = 0 NMP_LOOP1_OUT(NMP_COUNT);
+constexpr int LOOP1_NSFC2 = 0 NMP_LOOP1_SFC2(NMP_COUNT);
+static_assert(LOOP1_NOUT <= LOOP1_NCONST, "the results travel back in the rows that carried the constants");
+constexpr int LOOP1_ROWS = LOOP1_NCONST + LOOP1_NVAR + LOOP1_NSFC2;
+
+// Optional tail compaction (-DNMP_COMPACT_LOOP1): after NMP_COMPACT_AFTER passes the columns that still iterate are
+// packed into the first warps of the CTA through shared memory, so the rest of the tail runs on full warps.  Up to
+// NMP_COMPACT_CAP columns per CTA travel; the rest keep iterating in place.
 #ifdef NMP_COMPACT_LOOP1
-constexpr int LOOP1_CAP = (NMP_BLOCK * 3 / 8) < 136 ? (NMP_BLOCK * 3 / 8) : 136;   // static smem stays below 48 KB
+#ifndef NMP_COMPACT_CAP
+#define NMP_COMPACT_CAP 128
+#endif
+#ifndef NMP_COMPACT_AFTER
+#define NMP_COMPACT_AFTER 8
+#endif
+constexpr int LOOP1_CAP = NMP_COMPACT_CAP;
+// One packed column: its own function, so the register allocation of the kernel body does not see a second Loop1.
+template <class Opt>
+__device__ __noinline__ void loop1_job(const Opt& opt, float (*xch)[LOOP1_CAP], int t) {
+  Loop1 W;
+  W.mo.FM2 = 0.0f; W.mo.CH2 = 0.0f; W.THAIR = 0.0f; W.CZIL = 0.0f; W.WSTAR = 0.0f;   // dead (or opt_sfc = 2 only)
+  int w = 0;
+#define X(fld) W.fld = xch[w++][t];
+  NMP_LOOP1_CONST(X) NMP_LOOP1_VARF(X)
+#undef X
+#define X(fld) W.fld = __float_as_int(xch[w++][t]);
+  NMP_LOOP1_VARI(X)
+#undef X
+  if (opt.sfc == 2) {
+#define X(fld) W.fld = xch[w++][t];
+    NMP_LOOP1_SFC2(X)
+#undef X
+  }
+#pragma unroll 1
+  for (int iter = NMP_COMPACT_AFTER + 1; iter <= 20; ++iter) {
+    if (!W.running) break;
+    W.first(opt, iter);
+    W.second(iter);
+  }
+  w = 0;
+#define X(fld) xch[w++][t] = W.fld;
+  NMP_LOOP1_VARF(X)
+#undef X
+#define X(fld) xch[w++][t] = __int_as_float(W.fld);
+  NMP_LOOP1_VARI(X)
+#undef X
+#define X(fld) xch[w++][t] = W.fld;
+  NMP_LOOP1_OUT(X)
+#undef X
+  if (opt.sfc == 2) xch[LOOP1_ROWS - 1][t] = W.WSTAR;
+}
 #endif
 
 // =====================================================================================================
@@ -879,10 +932,15 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   }
   // ---- loop1 tail, passes 7..20 (only the lanes still iterating) --------------------------------------
 #ifdef NMP_COMPACT_LOOP1
+#pragma unroll 1
+  for (int iter = 7; iter <= NMP_COMPACT_AFTER; ++iter) {
+    if (!L.running) break;
+    L.first(opt, iter);
+    L.second(iter);
+  }
+  bool over_capacity = false;
   {
-    // optional tail compaction: columns that still iterate after pass 6 are packed into the first warps of the
-    // CTA through shared memory, so the tail runs on full warps instead of a few lanes per warp.
-    __shared__ float xch[LOOP1_WORDS][LOOP1_CAP];
+    __shared__ float xch[LOOP1_ROWS][LOOP1_CAP];
     __shared__ int xcnt;
     if (threadIdx.x == 0) xcnt = 0;
     __syncthreads();
@@ -893,64 +951,46 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     base = __shfl_sync(0xffffffffu, base, 0);
     const int slot = base + __popc(ball & ((1u << lane) - 1u));
     const bool moved = (L.running != 0) && slot < LOOP1_CAP;
+    over_capacity = (L.running != 0) && !moved;
     if (moved) {
       int w = 0;
 #define X(fld) xch[w++][slot] = L.fld;
-      NMP_LOOP1_FLOATS(X)
+      NMP_LOOP1_CONST(X) NMP_LOOP1_VARF(X)
 #undef X
 #define X(fld) xch[w++][slot] = __int_as_float(L.fld);
-      NMP_LOOP1_INTS(X)
+      NMP_LOOP1_VARI(X)
 #undef X
-      L.running = 0;
+      if (opt.sfc == 2) {
+#define X(fld) xch[w++][slot] = L.fld;
+        NMP_LOOP1_SFC2(X)
+#undef X
+      }
     }
     __syncthreads();
     const int njobs = xcnt < LOOP1_CAP ? xcnt : LOOP1_CAP;
-#pragma unroll 1
-    for (int job = 0; job < 2; ++job) {
-      // job 0: a packed column from the hand-off buffer; job 1: this thread's own column if it overflowed
-      const bool work = (job == 0) ? ((int)threadIdx.x < njobs) : (L.running != 0);
-      if (!__any_sync(0xffffffffu, work)) continue;
-      Loop1 W = L;
-      if (job == 0 && work) {
-        int w = 0;
-#define X(fld) W.fld = xch[w++][threadIdx.x];
-        NMP_LOOP1_FLOATS(X)
-#undef X
-#define X(fld) W.fld = __float_as_int(xch[w++][threadIdx.x]);
-        NMP_LOOP1_INTS(X)
-#undef X
-      }
-      if (!work) W.running = 0;
-#pragma unroll 1
-      for (int iter = 7; iter <= 20; ++iter) {
-        if (!W.running) break;
-        W.first(opt, iter);
-        W.second(iter);
-      }
-      if (work) {
-        if (job == 0) {
-          int w = 0;
-#define X(fld) xch[w++][threadIdx.x] = W.fld;
-          NMP_LOOP1_FLOATS(X)
-#undef X
-#define X(fld) xch[w++][threadIdx.x] = __int_as_float(W.fld);
-          NMP_LOOP1_INTS(X)
-#undef X
-        } else {
-          L = W;
-        }
-      }
-    }
+    if ((int)threadIdx.x < njobs) loop1_job(opt, xch, (int)threadIdx.x);
     __syncthreads();
     if (moved) {
       int w = 0;
 #define X(fld) L.fld = xch[w++][slot];
-      NMP_LOOP1_FLOATS(X)
+      NMP_LOOP1_VARF(X)
 #undef X
 #define X(fld) L.fld = __float_as_int(xch[w++][slot]);
-      NMP_LOOP1_INTS(X)
+      NMP_LOOP1_VARI(X)
 #undef X
+#define X(fld) L.fld = xch[w++][slot];
+      NMP_LOOP1_OUT(X)
+#undef X
+      if (opt.sfc == 2) L.WSTAR = xch[LOOP1_ROWS - 1][slot];
+      L.QSFC = (0.622f * L.EAH) / (L.SFCPRS - 0.378f * L.EAH);                            // func:2868, as in second()
     }
+  }
+  // over capacity (rare): the column keeps iterating in place
+#pragma unroll 1
+  for (int iter = NMP_COMPACT_AFTER + 1; iter <= 20; ++iter) {
+    if (!(over_capacity && L.running)) break;
+    L.first(opt, iter);
+    L.second(iter);
   }
 #else
 #pragma unroll 1
