@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- ctypes loader for the CPU parity oracle (oracle/src).
 
 Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs.  Nothing under noahmp_b200/ imports this module.  PARITY UNPINNED: see oracle/src/common.h.
+legs.  Nothing under noahmp_b200/ imports this module.  Parity pin: tests/golden/ref_*.npz, see oracle/src/common.h.
 """
 from __future__ import annotations
 

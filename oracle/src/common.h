@@ -1,9 +1,13 @@
 // TEST INFRASTRUCTURE ONLY -- CPU parity oracle for the Noah-MP column time step.
 //
-// PARITY UNPINNED: the reference (wk1984/noahmp-1) ships no golden vectors, no tests and
-// cannot be compiled here (no Fortran compiler; undefined wrf_* symbols).  This oracle is a
-// structurally 1:1 fp32 restatement of core/module_noahmp_func.f90 and is validated only by
-// the reference's own conservation checks (func:688-731) and leaf-routine known answers.
+// PARITY PIN: the reference (wk1984/noahmp-1) ships no golden vectors and no tests, and no Fortran compiler exists
+// in this image, so the Fortran cannot be run as it is.  Instead oracle/f90_to_cpp.py translates the reference's own
+// source (core/module_noahmp_*.f90, read where it lies) statement by statement into C++ under oracle/_ref/ (not in
+// git), and tests/golden/ref_*.npz hold that translation's outputs for every workload and every value of every option
+// (tools/make_reference_golden.py).  This hand-written restatement reproduces all of them BIT FOR BIT
+// (tests/test_reference_golden.py).  What the pin does not cover: a real Fortran compiler's code generation (it may
+// legally differ, e.g. GCC with -fno-math-errno rewrites cos(atan(x)), see Makefile) and the .TBL readers.
+// It is further checked by the reference's own conservation asserts (func:688-731) and leaf-routine known answers.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may build or load this.
 // The product (noahmp_b200/) never includes, links or calls anything under oracle/.

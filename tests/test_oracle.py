@@ -1,7 +1,6 @@
 """CPU oracle: leaf-routine known answers, the reference's own conservation pins (func:688-731) on every workload
-and option value, and the committed golden fixtures.  PARITY UNPINNED against the Fortran: the reference has no
-golden vectors and cannot be built; these tests pin the oracle to physics identities, to the
-reference's closure asserts and to itself."""
+and option value, and the committed regression fixtures.  The pin against the reference's own source is in
+tests/test_reference_golden.py; these tests add physics identities, the reference's closure asserts and self-consistency."""
 import ctypes as C
 import os
 
