@@ -99,3 +99,72 @@ def test_translator_covers_the_whole_module():
     assert len(meta["subs"]["noahmp_sflx"]) == 131                                   # func:66-91
     tracked = subprocess.run(["git", "ls-files", "oracle/_ref"], cwd=os.path.join(HERE, ".."), capture_output=True, text=True)
     assert tracked.stdout.strip() == ""
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference is not mounted here")
+def test_leaf_routines_match_the_translation_on_random_inputs(tables, oracle_libs):
+    """The routines the oracle exports one by one (esat, tdfcnd, frh2o, stomata, twostream, combo) against the
+    translated reference on inputs far outside what the workloads visit: every output bit."""
+    import ctypes as C
+    from oracle.refrun import RefModel
+    orc = Oracle(tables, synth.DEFAULT_OPTS)
+    ref = RefModel(tables, synth.DEFAULT_OPTS)
+    rng = np.random.default_rng(20240607)
+    f32, cf, P = np.float32, C.c_float, C.POINTER(C.c_float)
+    bits = lambda x: np.asarray(x, f32).view(np.int32)      # noqa: E731
+
+    for _ in range(400):                                                                     # esat, func:3692-3736
+        T = f32(rng.uniform(-60, 60))
+        out = (cf * 4)()
+        orc.lib.oracle_esat(cf(T), out)
+        _, r = ref.call("esat", dict(t=T))
+        assert np.array_equal(bits(list(out)), bits([r["esw"], r["esi"], r["desw"], r["desi"]]))
+    for _ in range(400):                                                                     # tdfcnd / frh2o
+        sl = int(rng.integers(1, 13))
+        smcmax = f32(tables.soil["SMCMAX"][sl - 1])
+        smc = f32(rng.uniform(0.02, 1.0)) * smcmax
+        sh2o = f32(rng.uniform(0.0, 1.0)) * smc
+        df = cf(0)
+        orc.lib.oracle_tdfcnd(orc.ctx, sl, cf(smc), cf(sh2o), C.byref(df))
+        _, r = ref.call("tdfcnd", dict(sltyp=sl, smc=smc, soilwat=sh2o))
+        assert bits(df.value) == bits(r["df"])
+        free = cf(0)
+        tk = f32(rng.uniform(240, 273.1))
+        orc.lib.oracle_frh2o(orc.ctx, sl, cf(tk), cf(smc), cf(sh2o), C.byref(free))
+        _, r = ref.call("frh2o", dict(sltyp=sl, tkelv=tk, smc=smc, soilwat=sh2o))
+        assert bits(free.value) == bits(r["free"])
+    for _ in range(400):                                                                     # stomata, func:3739-3887
+        v = dict(lutyp=int(rng.integers(1, 20)), igs=f32(rng.integers(0, 2)), sfcprs=f32(rng.uniform(6e4, 1.05e5)),
+                 sfctmp=f32(rng.uniform(260, 315)), apar=f32(rng.choice([0.0, rng.uniform(0, 400)])), tv=f32(rng.uniform(260, 320)),
+                 ea=f32(rng.uniform(100, 3000)), ei=f32(rng.uniform(200, 8000)), foln=f32(rng.uniform(0.2, 1.5)),
+                 btran=f32(rng.uniform(1e-6, 1)), rb=f32(rng.uniform(1, 300)))
+        v["o2"], v["co2"] = f32(0.209) * v["sfcprs"], f32(355e-6) * v["sfcprs"]
+        rs, psn, nit = cf(0), cf(0), C.c_int(0)
+        orc.lib.oracle_stomata(orc.ctx, v["lutyp"], cf(v["igs"]), cf(v["sfcprs"]), cf(v["sfctmp"]), cf(v["apar"]), cf(v["tv"]),
+                               cf(v["ea"]), cf(v["ei"]), cf(v["o2"]), cf(v["co2"]), cf(v["foln"]), cf(v["btran"]), cf(v["rb"]),
+                               C.byref(rs), C.byref(psn), C.byref(nit))
+        _, r = ref.call("stomata", v)
+        assert np.array_equal(bits([rs.value, psn.value]), bits([r["rs"], r["psn"]])), v
+    for _ in range(400):                                                                     # twostream, func:2215-2462
+        ib, ic = int(rng.integers(1, 3)), int(rng.integers(0, 2))
+        v = dict(lutyp=int(rng.choice([2, 5, 7, 8, 10, 11, 14, 15])), ib=ib, ic=ic, cosz=f32(rng.uniform(0.005, 1.0)),
+                 vai=f32(rng.choice([0.0, rng.uniform(0.05, 7.0)])), fwet=f32(rng.uniform(0, 1)), t=f32(rng.uniform(255, 300)),
+                 fveg=f32(rng.uniform(0.02, 1.0)), ist=1, iloc=1, jloc=1)
+        alb, rho, tau = (np.asarray(rng.uniform(lo, hi, 2), f32) for lo, hi in ((0.05, 0.8), (0.05, 0.5), (0.02, 0.3)))
+        out = (cf * 9)()
+        orc.lib.oracle_twostream(orc.ctx, v["lutyp"], ib, ic, cf(v["cosz"]), cf(v["vai"]), cf(v["fwet"]), cf(v["t"]),
+                                 alb.ctypes.data_as(P), alb.ctypes.data_as(P), rho.ctypes.data_as(P), tau.ctypes.data_as(P),
+                                 cf(v["fveg"]), out)
+        z = lambda: np.zeros(2, f32)                                                          # noqa: E731
+        v.update(albgrd=alb.copy(), albgri=alb.copy(), rho=rho.copy(), tau=tau.copy(), fab=z(), fre=z(), ftd=z(), fti=z(),
+                 frev=z(), freg=z(), gdir=f32(0), bgap=f32(0), wgap=f32(0))
+        _, r = ref.call("twostream", v)
+        got = [r[k][ib - 1] for k in ("fab", "fre", "ftd", "fti", "frev", "freg")] + [r["gdir"], r["bgap"], r["wgap"]]
+        assert np.array_equal(bits(list(out)), bits(got)), v
+    for _ in range(400):                                                                     # combo, func:5536-5577
+        a = np.asarray([rng.uniform(0.01, 0.5), rng.uniform(0, 20), rng.uniform(0.1, 100), rng.uniform(250, 273.16)], f32)
+        b = np.asarray([rng.uniform(0.01, 0.5), rng.uniform(0, 20), rng.uniform(0.1, 100), rng.uniform(250, 273.16)], f32)
+        a2 = a.copy()
+        orc.lib.oracle_combo(a2.ctypes.data_as(P), b.ctypes.data_as(P))
+        _, r = ref.call("combo", dict(dz=a[0], wliq=a[1], wice=a[2], t=a[3], dz2=b[0], wliq2=b[1], wice2=b[2], t2=b[3]))
+        assert np.array_equal(bits(a2), bits([r["dz"], r["wliq"], r["wice"], r["t"]]))
