@@ -207,10 +207,9 @@ def test_gpu_against_reference_fixtures(tables, variant, name):
     Every GPU build, every workload, every option value: layer count exact, prognostic state inside the north star's
     1e-4 (abs floor 1e-6) for >= 95 % of the columns of each plane (>= 90 % on the 64-column option cases: the canopy
     Newton loop amplifies last-ulp libm differences in a handful of columns, as it does between two CPU builds)."""
-    _, workload, ncol, nsteps, over = REF_CASES[name]
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.npz"))
-    opts = make_golden.options(over)
-    w = synth.make_workload(workload, ncol=ncol, nsteps=nsteps, opts=opts)
+    w, opts = make_reference_golden.case_workload(name)
+    ncol = w.ncol
     gs, _, gb = gpu_run(tables, w, synth.forcing_all(w), variant)
     assert int(gb[L.B["NFLAGGED"]]) == 0
     isn_same = (gs[L.S["ISNOW"]].view(np.int32) == g["state"][L.S["ISNOW"]].view(np.int32)).mean()
@@ -219,6 +218,18 @@ def test_gpu_against_reference_fixtures(tables, variant, name):
     for nm in TOL_PLANES:
         ok = frac_within(gs[L.S[nm]], g["state"][L.S[nm]], rel=1e-4 if ncol > 1 else 1e-3)
         assert ok >= floor, (nm, ok)
+
+
+@pytest.mark.parametrize("name", ["special_global", "special_snow"])
+def test_strict_bit_exact_on_special_surfaces(tables, oracle_libs, name):
+    """Urban, evergreen broadleaf, lake (IST=2), glacier (ICE=1), barren, tundra columns - types the generators never draw."""
+    w, opts = make_reference_golden.case_workload(name)
+    forcing = synth.forcing_all(w)
+    cs, cd, cflag = cpu_run(tables, w, forcing, "strict", diag=True)
+    gs, gd, gb = gpu_run(tables, w, forcing, "strict", diag=True)
+    assert int(gb[L.B["NFLAGGED"]]) == cflag == 0
+    assert np.array_equal(gs[:nplanes(opts)].view(np.int32), cs[:nplanes(opts)].view(np.int32))
+    assert ((gd.view(np.int32) == cd.view(np.int32)) | (np.isnan(gd) & np.isnan(cd))).all()
 
 
 # ---------------------------------------------------------------------------------------------- tier 3

@@ -35,11 +35,9 @@ def same_bits(a, b):
 
 
 def oracle_run(tables, name, variant):
-    _, workload, ncol, nsteps, over = CASES[name]
-    opts = make_golden.options(over)
-    w = synth.make_workload(workload, ncol=ncol, nsteps=nsteps, opts=opts)
+    w, opts = make_reference_golden.case_workload(name)
     state = w.state.copy()
-    diag = np.zeros((L.NDIAG, ncol), np.float32)
+    diag = np.zeros((L.NDIAG, w.ncol), np.float32)
     nflag = Oracle(tables, opts, fast=variant).run_workload(w, synth.forcing_all(w), diag, state=state)
     return state, diag[:58], nflag
 
@@ -61,7 +59,7 @@ def test_oracle_reproduces_the_reference_bit_for_bit(tables, oracle_libs, name):
     assert not bad_diag.any(), [L.DIAG[p] for p in np.where(bad_diag.any(axis=1))[0]]
 
 
-@pytest.mark.parametrize("name", ["uniform", "global", "snow", "conus", "noah_like"])
+@pytest.mark.parametrize("name", ["uniform", "global", "snow", "conus", "noah_like", "special_global"])
 def test_strict_oracle_is_the_same_model(tables, oracle_libs, name):
     """The strict twin (libm evaluated in fp64) is what the GPU strict build is compared with bit for bit; against the
     reference it may differ by last-ulp libm results amplified by the Newton loops: north-star tolerance 1e-4."""
@@ -78,10 +76,9 @@ def test_strict_oracle_is_the_same_model(tables, oracle_libs, name):
 
 
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference is not mounted here")
-@pytest.mark.parametrize("name", ["single", "conus", "snf3", "noah_like"])
+@pytest.mark.parametrize("name", ["single", "conus", "snf3", "noah_like", "special_snow"])
 def test_fixtures_are_what_the_translation_produces(name):
-    _, workload, ncol, nsteps, over = CASES[name]
-    _, state, diag, fatal = make_reference_golden.run_reference(workload, ncol, nsteps, over)
+    _, state, diag, fatal = make_reference_golden.run_reference(name)
     g = fixture(name)
     assert np.array_equal(fatal, g["fatal"])
     assert same_bits(state, g["state"]).all() and same_bits(diag, g["diag"]).all()

@@ -32,16 +32,33 @@ for _k, _vals in (("veg", (2, 3, 4, 5)), ("crs", (2,)), ("btr", (2, 3)), ("run",
     for _v in _vals:
         CASES.append((f"{_k}{_v}", "snow1m" if _k in ("frz", "snf", "alb", "stc", "tbot") else "global025", 64, 36, {_k: _v}))
 CASES.append(("noah_like", "global025", 64, 36, {"sfc": 2, "run": 3, "frz": 2, "inf": 2, "alb": 1, "tbot": 2, "stc": 2, "snf": 3}))
+# surface types the generators never draw: urban, evergreen broadleaf, lake (IST=2), glacier (ICE=1), barren, tundra, ...
+CASES += [("special_global", "global025", 120, 48, {}), ("special_snow", "snow1m", 120, 48, {})]
+SPECIAL_TYPES = [(1, 1, 0), (13, 1, 0), (16, 2, 0), (24, 1, 1), (19, 1, 0), (23, 1, 0), (20, 1, 0), (27, 1, 0)]   # lutyp, IST, ICE
 
 
-def run_reference(workload, ncol, nsteps, over, tables=None):
-    from oracle.refrun import RefModel
+def case_workload(name):
+    """The synthetic inputs of a case (rebuilt from the generators' seeds) and its option vector."""
+    _, workload, ncol, nsteps, over = next(c for c in CASES if c[0] == name)
     opts = make_golden.options(over)
-    t = tables or ParamTables.default()
     w = synth.make_workload(workload, ncol=ncol, nsteps=nsteps, opts=opts)
+    if name.startswith("special"):
+        si = w.static_i.copy()
+        for i in range(w.ncol):
+            lu, ist, ice = SPECIAL_TYPES[i % len(SPECIAL_TYPES)]
+            sl = 16 if ice else (14 if ist == 2 else (int(si[i]) >> 8) & 0xff)           # STAS: 16 = land ice, 14 = water
+            si[i] = L.pack_types(lu, sl, (int(si[i]) >> 16) & 0xff, (int(si[i]) >> 24) & 0xf, ist, ice)
+        w.static_i = si
+    return w, opts
+
+
+def run_reference(name, tables=None):
+    from oracle.refrun import RefModel
+    t = tables or ParamTables.default()
+    w, opts = case_workload(name)
     forcing = synth.forcing_all(w)
     state = w.state.copy()
-    diag = np.zeros((L.NDIAG, ncol), np.float32)
+    diag = np.zeros((L.NDIAG, w.ncol), np.float32)
     fatal = RefModel(t, opts).run(state, forcing, w.static_f, w.static_i, w.dt, synth.ZSOIL, w.julian0, w.yearlen, w.zref,
                                   w.co2_frac, w.o2_frac, w.foln, diag=diag)
     return w, state, diag[:58], fatal
@@ -52,7 +69,7 @@ def main():
     os.makedirs(out, exist_ok=True)
     for name, workload, ncol, nsteps, over in CASES:
         t0 = time.time()
-        w, state, diag, fatal = run_reference(workload, ncol, nsteps, over)
+        w, state, diag, fatal = run_reference(name)
         np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), state=state, diag=diag, fatal=fatal, opts=np.asarray(w.opts),
                             workload=workload, ncol=ncol, nsteps=nsteps)
         print(f"{name:12s} {workload:12s} {ncol:4d} x {nsteps:3d}  aborted columns {int(fatal.sum())}  TG mean "
