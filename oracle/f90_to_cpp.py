@@ -1081,6 +1081,70 @@ static inline float f_nan() { return std::numeric_limits<float>::quiet_NaN(); }
 '''
 
 
+# scalar prognostic arguments of noahmp_sflx that live in state planes, in the order refrun.py passes their plane numbers
+NATIVE_SCALARS = ["albold", "sneqvo", "tah", "eah", "fwet", "canliq", "canice", "tv", "tg", "qsfc", "qsnow", "snowh", "sneqv", "zwt",
+                  "wa", "wt", "wslake", "lfmass", "rtmass", "stmass", "wood", "stblcp", "fastcp", "lai", "sai", "cm", "ch", "tauss"]
+NATIVE_FORCING = ["sfctmp", "sfcprs", "uu", "vv", "q2", "soldn", "lwdn", "prcp", "cosz"]
+NATIVE_STATIC = ["lat", "shdfac", "tbot", "shdmax"]
+NATIVE_ARRAYS = [("stc", 7), ("zsnso", 7), ("soilwat", 4), ("smc", 4), ("snice", 3), ("snliq", 3)]
+
+
+def native_driver(tr, sub):
+    """A column loop in C++ around the translated noahmp_sflx (same duties as RefModel.run, OpenMP over columns): the
+    declarations and the call come from the parsed signature, the glue refers to the reference's argument names."""
+    e = tr.emit
+    e("struct RefRunParams { double julian0; float dt; float zsoil[4]; float zref, co2_frac, o2_frac, foln; int yearlen; };")
+    e('extern "C" long long ref_run_columns(long long ncol, int nsteps, float* state, const float* forcing, const float* static_f,')
+    e("    const int* static_i, float* diag, unsigned char* fatal, const RefRunParams* rp, const int* sp, const int* ap, int isnow_plane,")
+    e("    const int* fp, const int* cp) {")
+    e("  long long nfatal = 0;")
+    e("#pragma omp parallel for schedule(dynamic, 16) reduction(+ : nfatal)")
+    e("  for (long long i = 0; i < ncol; ++i) {")
+    for a in sub.args:
+        v = sub.vars[a]
+        if v.rank == 0:
+            e(f"    {v.ctype} {cname(a)}{{}};")
+    for nm, n in NATIVE_ARRAYS + [("zsoil", 4), ("ficeold", 3)]:
+        e(f"    float {nm}[{n}];")
+    e("    iloc = 1; jloc = 1; nsoil = 4; nsnow = 3; dt = rp->dt; foln = rp->foln; yearlen = rp->yearlen; zlvl = rp->zref;")
+    e("    for (int k = 0; k < 4; ++k) zsoil[k] = rp->zsoil[k];")
+    for k, nm in enumerate(NATIVE_STATIC):
+        e(f"    {nm} = static_f[(size_t)cp[{k}] * ncol + i];")
+    e("    { const int ty = static_i[i]; lutyp = ty & 0xff; sltyp = (ty >> 8) & 0xff; slptyp = (ty >> 16) & 0xff; isc = (ty >> 24) & 0xf;")
+    e("      ist = ((ty >> 28) & 1) + 1; ice = (ty >> 29) & 1; }")
+    for k, nm in enumerate(NATIVE_SCALARS):
+        e(f"    {cname(nm)} = state[(size_t)sp[{k}] * ncol + i];")
+    e("    memcpy(&isnow, &state[(size_t)isnow_plane * ncol + i], 4);")
+    for k, (nm, n) in enumerate(NATIVE_ARRAYS):
+        e(f"    for (int k = 0; k < {n}; ++k) {nm}[k] = state[(size_t)(ap[{k}] + k) * ncol + i];")
+    e("    bool dead = false;")
+    e("    for (int s = 0; s < nsteps && !dead; ++s) {")
+    for k, nm in enumerate(NATIVE_FORCING):
+        e(f"      {nm} = forcing[((size_t)s * {len(NATIVE_FORCING)} + fp[{k}]) * ncol + i];")
+    e("      psfc = sfcprs; co2air = rp->co2_frac * sfcprs; o2air = rp->o2_frac * sfcprs;")
+    e("      julian = (float)(rp->julian0 + (double)s * (double)rp->dt / 86400.0);")
+    e("      for (int k = -2; k <= 0; ++k) ficeold[k + 2] = (k >= isnow + 1) ? snice[k + 2] / (snice[k + 2] + snliq[k + 2]) : 0.0f;")
+    e("      try {")
+    e(f"        noahmp_sflx({', '.join(cname(a) for a in sub.args)});")
+    e("      } catch (const FFatal&) { dead = true; }")
+    e("    }")
+    e("    if (fatal) fatal[i] = dead;")
+    e("    if (dead) { nfatal += 1; continue; }")
+    for k, nm in enumerate(NATIVE_SCALARS):
+        e(f"    state[(size_t)sp[{k}] * ncol + i] = {cname(nm)};")
+    e("    memcpy(&state[(size_t)isnow_plane * ncol + i], &isnow, 4);")
+    for k, (nm, n) in enumerate(NATIVE_ARRAYS):
+        e(f"    for (int k = 0; k < {n}; ++k) state[(size_t)(ap[{k}] + k) * ncol + i] = {nm}[k];")
+    outs = [a for a in sub.args if sub.vars[a].intent == "out"]
+    e("    if (diag) {")
+    for k, nm in enumerate(outs):
+        e(f"      diag[(size_t){k} * ncol + i] = {cname(nm)};")
+    e("    }")
+    e("  }")
+    e("  return nfatal;")
+    e("}")
+
+
 def translate(ref_root: str, out_cpp: str, out_json: str):
     core = os.path.join(ref_root, "core")
     mods = {}
@@ -1110,6 +1174,7 @@ def translate(ref_root: str, out_cpp: str, out_json: str):
             continue
         tr.c_entry(s)
         sigs[s.name] = tr.sig_json(s)
+    native_driver(tr, tr.subs["noahmp_sflx"])
     tr.emit("}  // namespace ref")
     tr.emit(r'''
 extern "C" int ref_set(const char* name, const void* data, int count) {

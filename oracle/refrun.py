@@ -36,7 +36,7 @@ def build(ref_root: str = "/root/reference", force: bool = False, bounds: bool =
         from oracle import f90_to_cpp
         cpp = os.path.join(REFDIR, "noahmp_ref.cpp")
         f90_to_cpp.translate(ref_root, cpp, SIG)
-        cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", LIB, cpp]
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-w", "-o", LIB, cpp]
         if bounds:
             cmd.insert(1, "-DF_BOUNDS")
         subprocess.run(cmd, check=True)
@@ -211,6 +211,38 @@ class RefModel:
                 for p, nm in enumerate(out_names):
                     diag[p, i] = outs[nm]
         return fatal
+
+    def run_native(self, state, forcing, static_f, static_i, dt, zsoil, julian0, yearlen, zref, co2_frac, o2_frac, foln,
+                   diag=None, nthreads=0):
+        """Same contract as `run`, but the column loop is the generated C++ one (OpenMP): for big comparisons and timing."""
+        from noahmp_b200 import layout as L
+        from oracle.f90_to_cpp import NATIVE_ARRAYS, NATIVE_FORCING, NATIVE_SCALARS, NATIVE_STATIC
+
+        class RP(C.Structure):
+            _fields_ = [("julian0", C.c_double), ("dt", C.c_float), ("zsoil", C.c_float * 4), ("zref", C.c_float),
+                        ("co2_frac", C.c_float), ("o2_frac", C.c_float), ("foln", C.c_float), ("yearlen", C.c_int)]
+        nsteps, _, ncol = forcing.shape
+        assert state.flags.c_contiguous and forcing.flags.c_contiguous and state.dtype == np.float32
+        rp = RP(float(julian0), float(dt), (C.c_float * 4)(*[float(z) for z in zsoil]), float(zref), float(co2_frac), float(o2_frac),
+                float(foln), int(yearlen))
+        ia = lambda xs: np.asarray(xs, np.int32)                                 # noqa: E731
+        sp = ia([L.S[n.upper()] for n in NATIVE_SCALARS])
+        base = {"stc": L.stc(-2), "zsnso": L.zsnso(-2), "soilwat": L.soilwat(1), "smc": L.smc(1), "snice": L.snice(-2), "snliq": L.snliq(-2)}
+        ap = ia([base[n] for n, _ in NATIVE_ARRAYS])
+        fp = ia([L.F[n.upper()] for n in NATIVE_FORCING])
+        cp = ia([L.C[n.upper()] for n in NATIVE_STATIC])
+        fatal = np.zeros(ncol, np.uint8)
+        sf = np.ascontiguousarray(static_f, np.float32)
+        si = np.ascontiguousarray(static_i, np.int32)
+        if nthreads:
+            os.environ["OMP_NUM_THREADS"] = str(nthreads)
+        fn = self.lib.ref_run_columns
+        fn.restype = C.c_longlong
+        fn.argtypes = [C.c_longlong, C.c_int] + [C.c_void_p] * 6 + [C.POINTER(RP)] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2
+        fn(ncol, nsteps, state.ctypes.data, forcing.ctypes.data, sf.ctypes.data, si.ctypes.data,
+           diag.ctypes.data if diag is not None else None, fatal.ctypes.data, C.byref(rp), sp.ctypes.data, ap.ctypes.data,
+           int(L.S["ISNOW"]), fp.ctypes.data, cp.ctypes.data)
+        return fatal.astype(bool)
 
     def last_fatal(self) -> str:
         return self.lib.ref_last_fatal().decode()

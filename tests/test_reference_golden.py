@@ -165,3 +165,19 @@ def test_leaf_routines_match_the_translation_on_random_inputs(tables, oracle_lib
         orc.lib.oracle_combo(a2.ctypes.data_as(P), b.ctypes.data_as(P))
         _, r = ref.call("combo", dict(dz=a[0], wliq=a[1], wice=a[2], t=a[3], dz2=b[0], wliq2=b[1], wice2=b[2], t2=b[3]))
         assert np.array_equal(bits(a2), bits([r["dz"], r["wliq"], r["wice"], r["t"]]))
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference is not mounted here")
+def test_generated_column_loop_equals_the_per_call_driver(tables):
+    """The OpenMP column loop generated into the translation (used for the big live comparisons and for timing) gives
+    the same bits as the Python loop that calls noahmp_sflx once per column-step (used for the fixtures)."""
+    from oracle.refrun import RefModel
+    w, opts = make_reference_golden.case_workload("special_snow")
+    f = synth.forcing_all(w)
+    ref = RefModel(tables, opts)
+    args = (f, w.static_f, w.static_i, w.dt, synth.ZSOIL, w.julian0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
+    s1, d1 = w.state.copy(), np.zeros((L.NDIAG, w.ncol), np.float32)
+    s2, d2 = w.state.copy(), np.zeros((L.NDIAG, w.ncol), np.float32)
+    f1 = ref.run(s1, *args, diag=d1)
+    f2 = ref.run_native(s2, *args, diag=d2)
+    assert np.array_equal(f1, f2) and same_bits(s1, s2).all() and same_bits(d1[:58], d2[:58]).all()

@@ -5,6 +5,7 @@ any workload, any size, any options - beyond the committed fixtures.  Prints the
 
     python tools/compare_oracle_reference.py [--ncol N] [--steps S] [workload ...]       # default: all five
     python tools/compare_oracle_reference.py --ncol 24 --steps 8760 global025              # a whole year
+    python tools/compare_oracle_reference.py --options --ncol 2048                          # every value of every option
 """
 import os
 import sys
@@ -28,8 +29,8 @@ def compare(workload, ncol, nsteps, over, tables):
     f = synth.forcing_all(w)
     sr, dr = w.state.copy(), np.zeros((L.NDIAG, w.ncol), np.float32)
     t0 = time.time()
-    fatal = RefModel(tables, opts).run(sr, f, w.static_f, w.static_i, w.dt, synth.ZSOIL, w.julian0, w.yearlen, w.zref, w.co2_frac,
-                                       w.o2_frac, w.foln, diag=dr)
+    fatal = RefModel(tables, opts).run_native(sr, f, w.static_f, w.static_i, w.dt, synth.ZSOIL, w.julian0, w.yearlen, w.zref,
+                                              w.co2_frac, w.o2_frac, w.foln, diag=dr)     # generated C++ column loop, OpenMP
     so, do = w.state.copy(), np.zeros((L.NDIAG, w.ncol), np.float32)
     nf = Oracle(tables, opts).run_workload(w, f, diag=do, state=so)
     ok = ~fatal
@@ -55,6 +56,15 @@ def main():
             ncol, steps = (v, steps) if flag == "--ncol" else (ncol, v)
     t = ParamTables.default()
     total = 0
+    if "--options" in argv:
+        argv.remove("--options")
+        for k, vals in (("veg", (2, 3, 4, 5)), ("crs", (2,)), ("btr", (2, 3)), ("run", (2, 3, 4)), ("sfc", (2,)), ("frz", (2,)),
+                        ("inf", (2,)), ("rad", (2, 3)), ("alb", (1,)), ("snf", (2, 3)), ("tbot", (2,)), ("stc", (2,))):
+            for v in vals:
+                for wl in ("global025", "snow1m"):
+                    total += compare(wl, ncol, steps or 48, {k: v}, t)
+        print("TOTAL differing columns", total)
+        return 1 if total else 0
     for wl in argv or ["uniform100k", "global025", "snow1m", "conus1km", "single"]:
         total += compare(wl, 1 if wl == "single" else ncol, steps or {"uniform100k": 48, "conus1km": 24}.get(wl, 96), {}, t)
     print("TOTAL differing columns", total)
