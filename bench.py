@@ -191,6 +191,28 @@ def cpu_baseline(w, sample_cols: int, fast: bool = True, repeats: int = 1) -> di
                       f"({'-O3 AVX2+FMA' if fast else '-O2 no-FMA'} build of the C++ restatement, OpenMP static, {best:.2f} s)"}
 
 
+def translated_reference_leg(w, sample_cols: int = 200_000):
+    """The reference's own statements (mechanical Fortran -> C++ translation, oracle/_ref, -O2, OpenMP over columns) timed on a
+    smaller sample.  It is about half as fast as the hand-written port, so the port stays the baseline the GPU is set against
+    (the conservative choice); this figure is reported beside it.  None when oracle/_ref was not built (no /root/reference)."""
+    try:
+        from oracle import refrun
+        if not (os.path.exists(refrun.LIB) and os.path.exists(refrun.SIG)):
+            return None
+        ws, idx = sample_workload(w, sample_cols)
+        forcing = synth.forcing_all(ws, cols=idx)
+        ref = refrun.RefModel(ParamTables.default(), w.opts)
+        st = ws.state.copy()
+        t0 = time.perf_counter()
+        fatal = ref.run_native(st, forcing, ws.static_f, ws.static_i, w.dt, synth.ZSOIL, w.julian0, w.yearlen, w.zref, w.co2_frac,
+                               w.o2_frac, w.foln, nthreads=host_threads())
+        dt = time.perf_counter() - t0
+        return {"value": ws.ncol * w.nsteps / dt, "unit": UNIT, "cores": host_threads(), "kind": "reference (translated)",
+                "sample": f"{ws.ncol} columns x {w.nsteps} model steps, {dt:.2f} s, {int(fatal.sum())} columns aborted"}
+    except Exception as exc:  # the baseline legs must never take the bench line down
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -219,6 +241,9 @@ def run_reference(args):
                              "sample": f"every {w.ncol // n}-th column ({n} columns) x {w.nsteps} model steps per step (-O3 AVX2+FMA "
                                        "build of the C++ restatement; the reference Fortran cannot be compiled in this image)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    tr = translated_reference_leg(w)
+    if tr:
+        line["cpu_baseline"]["translated_reference"] = tr
     emit(line)
 
 
@@ -434,6 +459,9 @@ def run_ours(args):
                 "e2e": e2e, "e2e_state_roundtrip": e2e_rt, "other_variants": other, "aux_kernels": aux, "gpu_launches": int(launches), "clocks": clocks, "budget": bud}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_sample_cols)
+            tr = translated_reference_leg(w)
+            if tr:
+                line["cpu_baseline"]["translated_reference"] = tr
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = None
         emit(line)

@@ -36,7 +36,7 @@ def build(ref_root: str = "/root/reference", force: bool = False, bounds: bool =
         from oracle import f90_to_cpp
         cpp = os.path.join(REFDIR, "noahmp_ref.cpp")
         f90_to_cpp.translate(ref_root, cpp, SIG)
-        cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-w", "-o", LIB, cpp]
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-w", "-o", LIB, cpp]
         if bounds:
             cmd.insert(1, "-DF_BOUNDS")
         subprocess.run(cmd, check=True)
