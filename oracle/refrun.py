@@ -23,8 +23,10 @@ LIB = os.path.join(REFDIR, "libnoahmp_ref.so")
 SIG = os.path.join(REFDIR, "noahmp_ref.json")
 
 
-def build(ref_root: str = "/root/reference", force: bool = False, bounds: bool = False) -> str:
-    """Translate + compile.  Needs the reference sources; with only the prebuilt library present, returns it."""
+def build(ref_root: str = "/root/reference", force: bool = False, bounds: bool = False, keep_cpp: bool = False) -> str:
+    """Translate + compile.  Needs the reference sources; with only the prebuilt library present, returns it.
+    The generated C++ is a derived copy of reference source: it is deleted once compiled (keep_cpp=True to inspect it);
+    only the library and the signature table stay in oracle/_ref/ (git-ignored)."""
     src = os.path.join(ref_root, "core", "module_noahmp_func.f90")
     if not os.path.exists(src):
         if os.path.exists(LIB) and os.path.exists(SIG):
@@ -40,6 +42,8 @@ def build(ref_root: str = "/root/reference", force: bool = False, bounds: bool =
         if bounds:
             cmd.insert(1, "-DF_BOUNDS")
         subprocess.run(cmd, check=True)
+        if not keep_cpp:
+            os.remove(cpp)
     return LIB
 
 
