@@ -43,6 +43,7 @@ typedef struct noahmp_ctx noahmp_ctx;
 #define NOAHMP_FLAG_ZLVL    (1u << 4) /* func:3412-3415 */
 #define NOAHMP_FLAG_OPTVEG  (1u << 5) /* func:375-378  */
 #define NOAHMP_FLAG_NAN     (1u << 6) /* non-finite prognostic state (added) */
+#define NOAHMP_FLAG_BADTYPE (1u << 7) /* lutyp/sltyp/slptyp/ISC outside the tables (added): column left untouched */
 
 /* per-run scalars: the arguments of noahmp_sflx that do not vary per column (func:67-74) */
 typedef struct noahmp_run_params {
@@ -61,7 +62,7 @@ int noahmp_init(noahmp_ctx** ctx, int device);
 int noahmp_finalize(noahmp_ctx* ctx);
 /* Run on this CUDA stream (a cudaStream_t passed as void*); NULL = the legacy default stream. */
 int noahmp_set_stream(noahmp_ctx* ctx, void* cuda_stream);
-const char* noahmp_last_error(const noahmp_ctx* ctx);
+const char* noahmp_last_error(const noahmp_ctx* ctx);   /* ctx == NULL: text of the last failed noahmp_init */
 
 /* ---- options: replaces noahmp_set_options, core/module_noahmp_global.f90:77-112, same order:
  * veg, crs, btr, run, sfc, frz, inf, rad, alb, snf, tbot, stc.  Out-of-range values are rejected

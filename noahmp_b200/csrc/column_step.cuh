@@ -84,6 +84,11 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.S
     c.lutyp = ty & 0xff; c.sltyp = (ty >> 8) & 0xff; c.slptyp = (ty >> 16) & 0xff; c.ISC = (ty >> 24) & 0xf;
     c.IST = ((ty >> 28) & 1) + 1; c.ICE = (ty >> 29) & 1;
   }
+  // A type index outside the tables would read past them (the reference, without bounds checks, would too): such a column
+  // is flagged and left untouched; the arithmetic below runs on type 1 only so that the thread keeps step with its CTA.
+  const bool badtype = c.lutyp < 1 || c.lutyp > T.nvegtyp || c.sltyp < 1 || c.sltyp > T.nsoiltyp || c.ISC < 1 ||
+                       c.ISC > T.ncolor || c.slptyp < 1 || c.slptyp > NGEN - G_SLOPE;
+  if (badtype) { c.lutyp = 1; c.sltyp = 1; c.slptyp = 1; c.ISC = 1; }
   const float* VG = &T.veg[(c.lutyp - 1) * NVEGF];
   const int ISURBAN = T.flags[0], ISWATER = T.flags[1], ISBARREN = T.flags[2], ISICE = T.flags[3];
   const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
@@ -91,7 +96,7 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.S
   DiagSink<DIAG> dg;
   dg.base = DIAG ? a.diag + ii : nullptr;
   dg.stride = n;
-  unsigned anyflag = 0;
+  unsigned anyflag = badtype ? (unsigned)FLAG_BADTYPE : 0u;
   double b_errwat = 0.0, b_errabs = 0.0, b_errmax = 0.0, b_fsa = 0.0, b_fsr = 0.0, b_fira = 0.0, b_fsh = 0.0, b_lh = 0.0;
   double b_ssoil = 0.0, b_prcp = 0.0, b_et = 0.0, b_runoff = 0.0;
 
@@ -268,7 +273,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   }
 
   // ---- store the column -----------------------------------------------------------------------------
-  if (active) {
+  if (active && !badtype) {
     float* S = a.state + i;
     S[S_ALBOLD * n] = c.ALBOLD; S[S_SNEQVO * n] = c.SNEQVO; S[S_EAH * n] = c.EAH; S[S_FWET * n] = c.FWET;
     S[S_CANLIQ * n] = c.CANLIQ; S[S_CANICE * n] = c.CANICE; S[S_TV * n] = c.TV; S[S_TG * n] = c.TG;
@@ -286,7 +291,7 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(
 
   // ---- budget reduction: warp shuffle, one atomic per warp and quantity --------------------------------
   if (BUDGET) {
-    const double on = active ? 1.0 : 0.0;
+    const double on = (active && !badtype) ? 1.0 : 0.0;
     const double fin = (active && a.final_launch) ? 1.0 : 0.0;
     double soilw = 0.0;
 static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
@@ -294,11 +299,11 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       soilw += (double)(c.SMC[IX4(k)] * thick * 1000.0f);
     });
     double v[NBUDGET];
-    v[B_NCELL] = fin; v[B_NFLAGGED] = (anyflag != 0) ? on : 0.0; v[B_ERRWAT_SUM] = on * b_errwat;
+    v[B_NCELL] = fin; v[B_NFLAGGED] = (active && anyflag != 0) ? 1.0 : 0.0; v[B_ERRWAT_SUM] = on * b_errwat;
     v[B_ERRWAT_ABS] = on * b_errabs; v[B_ERRWAT_MAXABS] = on * b_errmax; v[B_FSA] = on * b_fsa; v[B_FSR] = on * b_fsr;
     v[B_FIRA] = on * b_fira; v[B_FSH] = on * b_fsh; v[B_LH] = on * b_lh; v[B_SSOIL] = on * b_ssoil;
     v[B_PRCP_DT] = on * b_prcp; v[B_ET_DT] = on * b_et; v[B_RUNOFF_DT] = on * b_runoff;
-    v[B_SNEQV] = fin * (double)c.sneqv; v[B_SOILWATER] = fin * soilw;
+    v[B_SNEQV] = fin * on * (double)c.sneqv; v[B_SOILWATER] = fin * on * soilw;
 static_for<0, (NBUDGET) - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
       const double r = (q == B_ERRWAT_MAXABS) ? warp_max(v[q]) : warp_sum(v[q]);
       if ((threadIdx.x & 31) == 0) {

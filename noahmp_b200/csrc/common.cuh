@@ -58,7 +58,7 @@ enum {
 };
 enum {
   FLAG_ERRSW = 1u << 0, FLAG_ERRENG = 1u << 1, FLAG_FIRE = 1u << 2, FLAG_HCAN = 1u << 3, FLAG_ZLVL = 1u << 4,
-  FLAG_OPTVEG = 1u << 5, FLAG_NAN = 1u << 6
+  FLAG_OPTVEG = 1u << 5, FLAG_NAN = 1u << 6, FLAG_BADTYPE = 1u << 7
 };
 
 // ---- packed parameter tables ----------------------------------------------------------------------

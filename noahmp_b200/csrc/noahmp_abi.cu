@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(256) synth_forcing_kernel(int64_t ncol, int64_
   forcing[F_COSZ * ncol + i] = cosz;
 }
 
+std::string g_init_error = "null context";   // text of the last failed noahmp_init (there is no context to hold it)
+
 int ensure(noahmp_ctx* c, void** p, size_t* cap, size_t need) {
   if (need <= *cap) return 0;
   if (*p) cudaFree(*p);
@@ -172,15 +174,12 @@ int noahmp_init(noahmp_ctx** out, int device) {
   noahmp_ctx* c = new noahmp_ctx();
   c->device = device;
   cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) {
-    fprintf(stderr, "noahmp_init: cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e));
-    delete c;
-    return -100 - (int)e;
-  }
-  e = cudaMalloc(&c->dev_tables, sizeof(Tables));
+  if (e == cudaSuccess) e = cudaMalloc(&c->dev_tables, sizeof(Tables));
   if (e == cudaSuccess) e = cudaMalloc(&c->dev_budget_scratch, sizeof(double) * NBUDGET);
-  if (e != cudaSuccess) {
-    fprintf(stderr, "noahmp_init: cudaMalloc: %s\n", cudaGetErrorString(e));
+  if (e != cudaSuccess) {   // no context to carry the text: noahmp_last_error(NULL) returns it
+    g_init_error = std::string("noahmp_init(device ") + std::to_string(device) + "): " + cudaGetErrorString(e);
+    cudaGetLastError();
+    if (c->dev_tables) cudaFree(c->dev_tables);
     delete c;
     return -100 - (int)e;
   }
@@ -210,7 +209,7 @@ int noahmp_set_stream(noahmp_ctx* c, void* s) {
   return 0;
 }
 
-const char* noahmp_last_error(const noahmp_ctx* c) { return c ? c->err.c_str() : "null context"; }
+const char* noahmp_last_error(const noahmp_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
 
 int noahmp_set_options(noahmp_ctx* c, const int o[12]) {
   if (!c || !o) return -1;

@@ -74,7 +74,7 @@ INT_DIAG_PLANES = [D["ITER"], D["FLAGS"]]
 
 # ---- error flag bits (one per fatal site of the reference) ----------------------
 FLAG_BITS = {"ERRSW": 1 << 0, "ERRENG": 1 << 1, "FIRE": 1 << 2, "HCAN": 1 << 3, "ZLVL": 1 << 4,
-             "OPTVEG": 1 << 5, "NAN": 1 << 6}
+             "OPTVEG": 1 << 5, "NAN": 1 << 6, "BADTYPE": 1 << 7}
 
 # ---- budget sums reduced on device (and all-reduced over ranks), fp64 ------------------------------
 BUDGET = ["NCELL", "NFLAGGED", "ERRWAT_SUM", "ERRWAT_ABS", "ERRWAT_MAXABS", "FSA", "FSR", "FIRA", "FSH", "LH",

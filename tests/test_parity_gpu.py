@@ -426,3 +426,25 @@ def test_api_misuse_is_reported_not_fatal(tables):
     torch.cuda.synchronize()
     assert int(bd[L.B["NFLAGGED"]].item()) == 32
     eng.close()
+
+
+def test_type_indices_outside_the_tables_are_flagged_not_fatal(tables):
+    """lutyp / sltyp / slope / colour indices beyond the tables (the reference would read past its arrays): the column
+    is flagged BADTYPE and left untouched, its neighbours are unaffected, the context stays usable."""
+    w = synth.make_workload("global025", ncol=512, nsteps=6)
+    forcing = synth.forcing_all(w)
+    good, _, gb0 = gpu_run(tables, w, forcing, "parity")
+    bad = {3: L.pack_types(255, 6, 1, 4, 1, 0), 100: L.pack_types(7, 0, 1, 4, 1, 0), 101: L.pack_types(7, 6, 31, 4, 1, 0),
+           500: L.pack_types(7, 6, 1, 0, 1, 0), 511: L.pack_types(0, 200, 1, 15, 1, 0)}
+    si = w.static_i.copy()
+    for i, v in bad.items():
+        si[i] = v
+    w.static_i = si
+    gs, gd, gb = gpu_run(tables, w, forcing, "parity", diag=True)
+    flags = gd[L.D["FLAGS"]].view(np.int32)
+    idx = np.asarray(sorted(bad))
+    assert (flags[idx] & L.FLAG_BITS["BADTYPE"]).all() and int(gb[L.B["NFLAGGED"]]) == len(bad) + int(gb0[L.B["NFLAGGED"]])
+    assert np.array_equal(gs[:, idx].view(np.int32), w.state[:, idx].view(np.int32))          # untouched
+    rest = np.setdiff1d(np.arange(w.ncol), idx)
+    assert np.array_equal(gs[:L.NSTATE_CORE, rest].view(np.int32), good[:L.NSTATE_CORE, rest].view(np.int32))
+    assert not (flags[rest] & L.FLAG_BITS["BADTYPE"]).any()
