@@ -40,6 +40,9 @@ FATAL_CALLS = {"wrf_error_fatal", "wrf_error_fatal3", "stop_program", "wrf_abort
 MESSAGE_CALLS = {"wrf_message", "wrf_debug"}
 
 
+REAL = "float"    # C++ type of Fortran `real`; translate(..., real_type="double") builds the fp64 twin (SURVEY 8c iv)
+
+
 def cname(n: str) -> str:
     return n + "_" if n in CPP_KEYWORDS else n
 
@@ -123,7 +126,7 @@ class Var:
 
     @property
     def ctype(self):
-        return {"real": "float", "double": "double", "integer": "int", "logical": "bool", "character": "const char*"}[self.ftype]
+        return {"real": REAL, "double": "double", "integer": "int", "logical": "bool", "character": "const char*"}[self.ftype]
 
     @property
     def rank(self):
@@ -333,7 +336,7 @@ TOKEN_RE = re.compile(r"""
 
 INTRINSIC_1 = {"sqrt": "f_sqrt", "exp": "f_exp", "log": "f_log", "alog": "f_log", "log10": "f_log10", "alog10": "f_log10",
                "tanh": "f_tanh", "atan": "f_atan", "cos": "f_cos", "sin": "f_sin", "tan": "f_tan", "acos": "f_acos",
-               "asin": "f_asin", "abs": "f_abs", "nint": "f_nint", "float": "(float)", "dble": "(double)", "sngl": "(float)",
+               "asin": "f_asin", "abs": "f_abs", "nint": "f_nint", "float": "F_REAL", "dble": "(double)", "sngl": "F_REAL",
                "aint": "f_aint", "anint": "f_anint", "floor": "f_floor", "ceiling": "f_ceiling", "isnan": "f_isnan"}
 
 
@@ -471,7 +474,9 @@ class ExprTranslator:
             mant = "0" + mant
         txt = mant + (f"e{ex}" if ex is not None else "")
         dbl = ech == "d" or kind in ("r8", "8")
-        return txt if dbl else txt + "f"
+        if dbl:
+            return txt
+        return txt + "f" if REAL == "float" else f"((double){txt}f)"
 
     def p_args(self):
         """Parse '(' a, b, lo:hi ')' -> list of str | Section-bounds tuples."""
@@ -572,7 +577,7 @@ class ExprTranslator:
         if name == "real":
             if len(args) == 2 and args[1].strip("()") in ("r8", "8"):
                 return f"(double)({args[0]})"
-            return f"(float)({args[0]})"
+            return f"F_REAL({args[0]})"
         if name == "mod" and len(args) == 2:
             return f"f_mod({args[0]}, {args[1]})"
         if name == "sign" and len(args) == 2:
@@ -987,6 +992,10 @@ RUNTIME = r'''// GENERATED by oracle/f90_to_cpp.py from the reference's Fortran 
 #include <type_traits>
 #include <vector>
 
+#ifndef F_REAL_T
+#define F_REAL_T float
+#endif
+#define F_REAL(x) ((F_REAL_T)(x))
 struct FFatal { std::string what; };
 static std::string last_fatal;
 [[noreturn]] static void f_fatal(const char* msg) { throw FFatal{msg}; }
@@ -1065,18 +1074,25 @@ static inline int f_abs(int x) { return x < 0 ? -x : x; }
 static inline int f_nint(float x) { return (int)lroundf(x); }
 static inline int f_nint(double x) { return (int)lround(x); }
 static inline int f_floor(float x) { return (int)floorf(x); }
+static inline int f_floor(double x) { return (int)floor(x); }
 static inline int f_ceiling(float x) { return (int)ceilf(x); }
+static inline int f_ceiling(double x) { return (int)ceil(x); }
 static inline bool f_isnan(float x) { return x != x; }
+static inline bool f_isnan(double x) { return x != x; }
 static inline float f_atan2(float y, float x) { return atan2f(y, x); }
+static inline double f_atan2(double y, double x) { return atan2(y, x); }
+static inline double f_pow(int x, double y) { return pow((double)x, y); }
 template <class A, class B> static inline typename std::common_type<A, B>::type f_max(A a, B b) {
   typedef typename std::common_type<A, B>::type T; return (T)a > (T)b ? (T)a : (T)b; }
 template <class A, class B> static inline typename std::common_type<A, B>::type f_min(A a, B b) {
   typedef typename std::common_type<A, B>::type T; return (T)a < (T)b ? (T)a : (T)b; }
 static inline int f_mod(int a, int b) { return a % b; }
 static inline float f_mod(float a, float b) { return fmodf(a, b); }
+static inline double f_mod(double a, double b) { return fmod(a, b); }
 static inline float f_sign(float a, float b) { return copysignf(fabsf(a), b); }
+static inline double f_sign(double a, double b) { return copysign(fabs(a), b); }
 static inline int f_sign(int a, int b) { return b >= 0 ? (a < 0 ? -a : a) : -(a < 0 ? -a : a); }
-static inline float f_nan() { return std::numeric_limits<float>::quiet_NaN(); }
+static inline F_REAL_T f_nan() { return std::numeric_limits<F_REAL_T>::quiet_NaN(); }
 
 '''
 
@@ -1105,7 +1121,7 @@ def native_driver(tr, sub):
         if v.rank == 0:
             e(f"    {v.ctype} {cname(a)}{{}};")
     for nm, n in NATIVE_ARRAYS + [("zsoil", 4), ("ficeold", 3)]:
-        e(f"    float {nm}[{n}];")
+        e(f"    {REAL} {nm}[{n}];")
     e("    iloc = 1; jloc = 1; nsoil = 4; nsnow = 3; dt = rp->dt; foln = rp->foln; yearlen = rp->yearlen; zlvl = rp->zref;")
     e("    for (int k = 0; k < 4; ++k) zsoil[k] = rp->zsoil[k];")
     for k, nm in enumerate(NATIVE_STATIC):
@@ -1115,6 +1131,7 @@ def native_driver(tr, sub):
     for k, nm in enumerate(NATIVE_SCALARS):
         e(f"    {cname(nm)} = state[(size_t)sp[{k}] * ncol + i];")
     e("    memcpy(&isnow, &state[(size_t)isnow_plane * ncol + i], 4);")
+    e("    // (fp64 twin: the planes stay fp32 at the boundary, everything between load and store is double)")
     for k, (nm, n) in enumerate(NATIVE_ARRAYS):
         e(f"    for (int k = 0; k < {n}; ++k) {nm}[k] = state[(size_t)(ap[{k}] + k) * ncol + i];")
     e("    bool dead = false;")
@@ -1123,7 +1140,7 @@ def native_driver(tr, sub):
         e(f"      {nm} = forcing[((size_t)s * {len(NATIVE_FORCING)} + fp[{k}]) * ncol + i];")
     e("      psfc = sfcprs; co2air = rp->co2_frac * sfcprs; o2air = rp->o2_frac * sfcprs;")
     e("      julian = (float)(rp->julian0 + (double)s * (double)rp->dt / 86400.0);")
-    e("      for (int k = -2; k <= 0; ++k) ficeold[k + 2] = (k >= isnow + 1) ? snice[k + 2] / (snice[k + 2] + snliq[k + 2]) : 0.0f;")
+    e(f"      for (int k = -2; k <= 0; ++k) ficeold[k + 2] = (k >= isnow + 1) ? snice[k + 2] / (snice[k + 2] + snliq[k + 2]) : ({REAL})0;")
     e("      try {")
     e(f"        noahmp_sflx({', '.join(cname(a) for a in sub.args)});")
     e("      } catch (const FFatal&) { dead = true; }")
@@ -1131,21 +1148,23 @@ def native_driver(tr, sub):
     e("    if (fatal) fatal[i] = dead;")
     e("    if (dead) { nfatal += 1; continue; }")
     for k, nm in enumerate(NATIVE_SCALARS):
-        e(f"    state[(size_t)sp[{k}] * ncol + i] = {cname(nm)};")
+        e(f"    state[(size_t)sp[{k}] * ncol + i] = (float){cname(nm)};")
     e("    memcpy(&state[(size_t)isnow_plane * ncol + i], &isnow, 4);")
     for k, (nm, n) in enumerate(NATIVE_ARRAYS):
-        e(f"    for (int k = 0; k < {n}; ++k) state[(size_t)(ap[{k}] + k) * ncol + i] = {nm}[k];")
+        e(f"    for (int k = 0; k < {n}; ++k) state[(size_t)(ap[{k}] + k) * ncol + i] = (float){nm}[k];")
     outs = [a for a in sub.args if sub.vars[a].intent == "out"]
     e("    if (diag) {")
     for k, nm in enumerate(outs):
-        e(f"      diag[(size_t){k} * ncol + i] = {cname(nm)};")
+        e(f"      diag[(size_t){k} * ncol + i] = (float){cname(nm)};")
     e("    }")
     e("  }")
     e("  return nfatal;")
     e("}")
 
 
-def translate(ref_root: str, out_cpp: str, out_json: str):
+def translate(ref_root: str, out_cpp: str, out_json: str, real_type: str = "float"):
+    global REAL
+    REAL = real_type
     core = os.path.join(ref_root, "core")
     mods = {}
     for fn, want in (("module_noahmp_const.f90", False), ("module_noahmp_global.f90", True),
@@ -1154,7 +1173,7 @@ def translate(ref_root: str, out_cpp: str, out_json: str):
         m = parse_file(os.path.join(core, fn), want_subs=want)
         mods[m.name] = m
     tr = Translator(mods)
-    tr.out.append(RUNTIME)
+    tr.out.append(f"#define F_REAL_T {real_type}\n" + RUNTIME)
     tr.emit("namespace ref {")
     for m in mods.values():
         tr.emit(f"// ---- module {m.name}")
@@ -1181,6 +1200,10 @@ extern "C" int ref_set(const char* name, const void* data, int count) {
   for (ref::RegEntry* e = ref::registry; e->name; ++e)
     if (!strcmp(e->name, name)) {
       if (count != e->count) return -2;
+      if (e->type == 0 && sizeof(F_REAL_T) == 8) {          // fp64 twin: `real` module variables are doubles, the caller sends floats
+        for (int k = 0; k < count; ++k) ((double*)e->ptr)[k] = (double)((const float*)data)[k];
+        return 0;
+      }
       memcpy(e->ptr, data, (size_t)count * (e->type == 2 ? 8 : 4));
       return 0;
     }

@@ -20,31 +20,34 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFDIR = os.path.join(HERE, "_ref")
 LIB = os.path.join(REFDIR, "libnoahmp_ref.so")
+LIB64 = os.path.join(REFDIR, "libnoahmp_ref64.so")     # the fp64 twin: same statements, every `real` a double
 SIG = os.path.join(REFDIR, "noahmp_ref.json")
 
 
-def build(ref_root: str = "/root/reference", force: bool = False, bounds: bool = False, keep_cpp: bool = False) -> str:
+def build(ref_root: str = "/root/reference", force: bool = False, bounds: bool = False, keep_cpp: bool = False,
+          fp64: bool = False) -> str:
     """Translate + compile.  Needs the reference sources; with only the prebuilt library present, returns it.
     The generated C++ is a derived copy of reference source: it is deleted once compiled (keep_cpp=True to inspect it);
     only the library and the signature table stay in oracle/_ref/ (git-ignored)."""
     src = os.path.join(ref_root, "core", "module_noahmp_func.f90")
+    lib = LIB64 if fp64 else LIB
     if not os.path.exists(src):
-        if os.path.exists(LIB) and os.path.exists(SIG):
-            return LIB
-        raise FileNotFoundError(f"{src} not found and no prebuilt {LIB}")
+        if os.path.exists(lib) and os.path.exists(SIG):
+            return lib
+        raise FileNotFoundError(f"{src} not found and no prebuilt {lib}")
     tool = os.path.join(HERE, "f90_to_cpp.py")
-    stale = force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(tool), os.path.getmtime(src))
+    stale = force or not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(tool), os.path.getmtime(src))
     if stale:
         from oracle import f90_to_cpp
-        cpp = os.path.join(REFDIR, "noahmp_ref.cpp")
-        f90_to_cpp.translate(ref_root, cpp, SIG)
-        cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-w", "-o", LIB, cpp]
+        cpp = os.path.join(REFDIR, "noahmp_ref64.cpp" if fp64 else "noahmp_ref.cpp")
+        f90_to_cpp.translate(ref_root, cpp, SIG, real_type="double" if fp64 else "float")
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-w", "-o", lib, cpp]
         if bounds:
             cmd.insert(1, "-DF_BOUNDS")
         subprocess.run(cmd, check=True)
         if not keep_cpp:
             os.remove(cpp)
-    return LIB
+    return lib
 
 
 _CT = {"real": C.c_float, "integer": C.c_int, "double": C.c_double, "logical": C.c_bool}
@@ -52,9 +55,11 @@ _NP = {"real": np.float32, "integer": np.int32, "double": np.float64, "logical":
 
 
 class RefModel:
-    def __init__(self, tables, opts, ref_root: str = "/root/reference"):
-        build(ref_root)
-        self.lib = C.CDLL(LIB)
+    def __init__(self, tables, opts, ref_root: str = "/root/reference", fp64: bool = False):
+        """fp64=True loads the twin in which every `real` is a double (constants keep their fp32 values): only
+        `run_native` may be used with it (planes stay fp32 at the boundary)."""
+        self.fp64 = fp64
+        self.lib = C.CDLL(build(ref_root, fp64=fp64))
         self.lib.ref_set.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         self.lib.ref_last_fatal.restype = C.c_char_p
         meta = json.load(open(SIG))
@@ -131,6 +136,7 @@ class RefModel:
     def call(self, sub: str, values: dict):
         """Call a translated subroutine; `values` maps dummy-argument names to scalars / numpy arrays (arrays are
         updated in place, scalars are returned in the result dict)."""
+        assert not self.fp64, "per-call interface is fp32 only"
         sig = self.sigs[sub]
         holders, ptrs = [], (C.c_void_p * len(sig))()
         for k, a in enumerate(sig):

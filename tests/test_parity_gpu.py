@@ -220,6 +220,25 @@ def test_gpu_against_reference_fixtures(tables, variant, name):
         assert ok >= floor, (nm, ok)
 
 
+@pytest.mark.parametrize("variant", ["strict", "parity", "fast"])
+@pytest.mark.parametrize("name", make_reference_golden.FP64_CASES)
+def test_gpu_error_against_the_fp64_twin(tables, variant, name):
+    """Distance to the fp64 evaluation of the reference's statements (tests/golden/ref64_*.npz): a GPU build may be at most
+    4x as far from it as the fp32 reference itself is (95th percentile over columns per slow plane, floor 2e-6 relative)."""
+    g32 = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.npz"))["state"]
+    g64 = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref64_{name}.npz"))["state"]
+    w, opts = make_reference_golden.case_workload(name)
+    gs, _, _ = gpu_run(tables, w, synth.forcing_all(w), variant)
+
+    def q95(a, b):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        return float(np.quantile(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-3), 0.95))
+    for nm in ["TG", "TV", "STC+1", "STC+4", "SMC1", "SMC4", "SOILWAT1", "ZWT", "WA", "SNEQV", "SNOWH"]:
+        p = L.S[nm]
+        ours, theirs = q95(gs[p], g64[p]), q95(g32[p], g64[p])
+        assert ours <= 4.0 * theirs + 2e-6, (nm, ours, theirs)
+
+
 @pytest.mark.parametrize("name", ["special_global", "special_snow"])
 def test_strict_bit_exact_on_special_surfaces(tables, oracle_libs, name):
     """Urban, evergreen broadleaf, lake (IST=2), glacier (ICE=1), barren, tundra columns - types the generators never draw."""

@@ -45,6 +45,31 @@ def oracle_run(tables, name, variant):
 def test_every_case_has_a_fixture():
     have = {os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(HERE, "golden", "ref_*.npz"))}
     assert have == set(CASES)
+    have64 = {os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(HERE, "golden", "ref64_*.npz"))}
+    assert have64 == set(make_reference_golden.FP64_CASES)
+
+
+def rel_err(a, b, floor):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+
+
+SLOW_PLANES = ["TG", "TV", "STC+1", "STC+2", "STC+3", "STC+4", "SMC1", "SMC2", "SMC3", "SMC4", "SOILWAT1", "SOILWAT4", "ZWT", "WA", "WT",
+               "SNEQV", "SNOWH"]
+
+
+@pytest.mark.parametrize("name", make_reference_golden.FP64_CASES)
+def test_fp32_rounding_noise_of_the_reference_itself(name):
+    """tests/golden/ref64_*.npz: the reference's statements with every `real` a double.  After 24-96 steps the fp32
+    reference is within 5e-5 of it (95th percentile over columns, slow prognostic planes; most sit near 1e-6) - except the
+    liquid water of frozen soil, where the supercooled-water power law of a small temperature difference (func:4373-4387)
+    puts the reference's OWN fp32 noise at 0.3-1.3e-4.  The north star's 1e-4 is therefore at the level of the reference's
+    rounding noise, not an allowance for sloppiness."""
+    r32, r64 = fixture(name)["state"], np.load(os.path.join(HERE, "golden", f"ref64_{name}.npz"))["state"]
+    assert np.array_equal(r32[L.S["ISNOW"]].view(np.int32), r64[L.S["ISNOW"]].view(np.int32))
+    for nm in SLOW_PLANES:
+        e = rel_err(r32[L.S[nm]], r64[L.S[nm]], 1e-3)
+        assert np.quantile(e, 0.95) <= (5e-4 if nm.startswith("SOILWAT") else 5e-5), (nm, float(np.quantile(e, 0.95)))
 
 
 @pytest.mark.parametrize("name", list(CASES))

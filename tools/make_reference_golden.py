@@ -64,9 +64,28 @@ def run_reference(name, tables=None):
     return w, state, diag[:58], fatal
 
 
+FP64_CASES = ["uniform", "global", "snow", "conus", "special_global", "special_snow"]
+
+
+def run_reference_fp64(name, tables=None):
+    """The same statements with every `real` a double (constants keep their fp32 values): the yardstick for how much of a
+    difference is fp32 rounding noise (SURVEY 8c iv).  End state rounded to fp32 planes."""
+    from oracle.refrun import RefModel
+    t = tables or ParamTables.default()
+    w, opts = case_workload(name)
+    state = w.state.copy()
+    fatal = RefModel(t, opts, fp64=True).run_native(state, synth.forcing_all(w), w.static_f, w.static_i, w.dt, synth.ZSOIL, w.julian0,
+                                                    w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
+    return w, state, fatal
+
+
 def main():
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
+    for name in FP64_CASES:
+        w, state, fatal = run_reference_fp64(name)
+        np.savez_compressed(os.path.join(out, f"ref64_{name}.npz"), state=state, fatal=fatal)
+        print(f"{name:12s} fp64 twin: aborted columns {int(fatal.sum())}  TG mean {float(state[L.S['TG']].mean()):.3f}", flush=True)
     for name, workload, ncol, nsteps, over in CASES:
         t0 = time.time()
         w, state, diag, fatal = run_reference(name)
