@@ -130,8 +130,11 @@ def columns_from_init(path: str, tables: ParamTables) -> Columns:
     sf[L.C["TBOT"]] = get("tbot", 285.0)
     sf[L.C["SHDMAX"]] = get("shdmax", 0.8)
     ones = np.ones(n, np.int64)
-    si = L.pack_types(z["lutyp"].astype(np.int64), sl, z["slptyp"].astype(np.int64) if "slptyp" in z.files else ones,
-                      z["isc"].astype(np.int64) if "isc" in z.files else 4 * ones, ones, 0 * ones).astype(np.int32)
+    lut = z["lutyp"].astype(np.int64)
+    ist = np.where(lut == tables.flags["ISWATER"], 2, 1)          # IST: 1 soil, 2 lake (func:117)
+    ice = np.where(lut == tables.flags["ISICE"], 1, 0)            # ICE: 1 land ice (func:116)
+    si = L.pack_types(lut, sl, z["slptyp"].astype(np.int64) if "slptyp" in z.files else ones,
+                      z["isc"].astype(np.int64) if "isc" in z.files else 4 * ones, ist, ice).astype(np.int32)
     return Columns(st, sf, si, lat, lon)
 
 
