@@ -35,7 +35,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-DNMP_PHASE_BARRIERS"]
 VARIANTS = {
     "parity": ("libnoahmp_b200.so", ["-fmad=false", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
-    "fast": ("libnoahmp_b200_fast.so", ["--use_fast_math", "-DNMP_BLOCK=256", "-DNMP_MIN_BLOCKS=2"]),
+    "fast": ("libnoahmp_b200_fast.so", ["--use_fast_math", "-DNMP_FAST_ALGEBRA", "-DNMP_BLOCK=256", "-DNMP_MIN_BLOCKS=3",
+                                        "-DNMP_SYNC_MASK=0x7f7afu"]),
     "strict": ("libnoahmp_b200_strict.so", ["-fmad=false", "-DNMP_CR_LIBM", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
 }
 

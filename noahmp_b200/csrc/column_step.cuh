@@ -48,7 +48,6 @@ __global__ void __launch_bounds__(NMP_BLOCK, NMP_MIN_BLOCKS) column_step_kernel(
     for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < a.ncol;
   const int64_t ii = active ? i : a.ncol - 1;   // tail threads shadow the last column, never store

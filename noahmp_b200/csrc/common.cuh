@@ -159,6 +159,10 @@ __device__ __forceinline__ float m_soilpowf(float x, float y) { return __nv_powf
 #else
 __device__ __forceinline__ float m_soilpowf(float x, float y) { return m_powf(x, y); }
 #endif
+#if defined(NMP_FAST_ALGEBRA) && !defined(NMP_CR_LIBM)
+extern "C" __device__ float __nv_powf(float, float);
+__device__ __forceinline__ float m_accpowf(float x, float y) { return __nv_powf(x, y); }
+#endif
 NMP_LIBM1(expf, exp)
 NMP_LIBM1(logf, log)
 NMP_LIBM1(log10f, log10)

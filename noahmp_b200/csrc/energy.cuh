@@ -107,11 +107,19 @@ __device__ __forceinline__ void sfcdif1(int iter, float SFCTMP, float RHOAIR, fl
     MOZ2 = 0.0f;
   } else {
     const float TVIR = (1.0f + 0.61f * QAIR) * SFCTMP;
+#ifdef NMP_FAST_ALGEBRA   // one reciprocal instead of the chain /TVIR, /(RHOAIR CPAIR), /TMP1, /MOL
+    float TMP1 = H * ((KARMAN * GRAV) / (TVIR * (RHOAIR * CPAIR)));
+    if (fabsf(TMP1) <= MPE) TMP1 = MPE;
+    const float RMOL = -TMP1 / cube(m.FV);
+    m.MOZ = fmin2((ZLVL - ZPD) * RMOL, 1.0f);
+    MOZ2 = fmin2((2.0f + Z0H) * RMOL, 1.0f);
+#else
     float TMP1 = KARMAN * (GRAV / TVIR) * H / (RHOAIR * CPAIR);
     if (fabsf(TMP1) <= MPE) TMP1 = MPE;
     const float MOL = -1.0f * cube(m.FV) / TMP1;
     m.MOZ = fmin2((ZLVL - ZPD) / MOL, 1.0f);
     MOZ2 = fmin2((2.0f + Z0H) / MOL, 1.0f);
+#endif
   }
   if (MOZOLD * m.MOZ < 0.0f) m.MOZSGN = m.MOZSGN + 1;                                     // func:3438-3446
   if (m.MOZSGN >= 2) {
@@ -152,9 +160,16 @@ __device__ __forceinline__ void sfcdif1(int iter, float SFCTMP, float RHOAIR, fl
   if (fabsf(CHFH) <= MPE) CHFH = MPE;
   if (fabsf(CM2FM2) <= MPE) CM2FM2 = MPE;
   if (fabsf(CH2FH2) <= MPE) CH2FH2 = MPE;
+#ifdef NMP_FAST_ALGEBRA   // sqrt(K^2 / CMFM^2) = K / |CMFM|: two independent reciprocals, no square root
+  const float RCMFM = 1.0f / CMFM;
+  m.CM = (KARMAN * KARMAN) * RCMFM * RCMFM;
+  m.CH = (KARMAN * KARMAN) * RCMFM / CHFH;
+  m.FV = UR * (KARMAN * fabsf(RCMFM));
+#else
   m.CM = KARMAN * KARMAN / (CMFM * CMFM);                                                 // func:3499-3506
   m.CH = KARMAN * KARMAN / (CMFM * CHFH);
   m.FV = UR * sqrtf(m.CM);
+#endif
   m.CH2 = KARMAN * m.FV / CH2FH2;
 }
 
@@ -262,12 +277,23 @@ struct Stomata {
     }
     psn = fmin2(fmin2(wj, wc), we) * igs;
     const float cs = fmax2(co2 - 1.37f * rlb * sfcprs * psn, MPE);
+#ifdef NMP_FAST_ALGEBRA   // shared reciprocal of cs, one reciprocal for the two roots
+    const float mpc = L.MP * psn * sfcprs / cs;
+    const float a = mpc * (ea / ei) + L.BP;
+    const float b = (mpc + L.BP) * rlb - 1.0f;
+    const float c = -rlb;
+    const float disc = sqrtf(b * b - 4.0f * a * c);
+    const float q = (b >= 0.0f) ? -0.5f * (b + disc) : -0.5f * (b - disc);
+    const float raq = 1.0f / (a * q);
+    rs = fmax2(q * q * raq, c * a * raq);
+#else
     const float a = L.MP * psn * sfcprs * ea / (cs * ei) + L.BP;
     const float b = (L.MP * psn * sfcprs / cs + L.BP) * rlb - 1.0f;
     const float c = -rlb;
     const float disc = sqrtf(b * b - 4.0f * a * c);
     const float q = (b >= 0.0f) ? -0.5f * (b + disc) : -0.5f * (b - disc);
     rs = fmax2(q / a, c / q);
+#endif
     const float fci = fmax2(cs - psn * sfcprs * 1.65f * rs, 0.0f);
     if (((cihigh - cilow) <= 5.0E-2f) || fabsf(fci - ci) <= MPE) done = true;
     else if (fci > ci) cilow = ci;
@@ -368,6 +394,49 @@ __device__ __forceinline__ void twostream_band(const TwoStreamCommon& t, int IC,
   const float H = sqrtf(TMP1) / t.AVMU;
   float SIGMA = TMP0 * TMP0 - TMP1;
   if (fabsf(SIGMA) < 1.e-6f) SIGMA = copysignf(1.e-6f, SIGMA);
+#ifdef NMP_FAST_ALGEBRA
+  const float AH = t.AVMU * H;
+  const float P1 = B + AH, P2 = B - AH, P3 = B + TMP0, P4 = B - TMP0;
+  const float S1 = m_expf(-H * VAI);
+  const float S2 = m_expf(-t.EXT * VAI);
+  const float ALB = (IC == 0) ? ALBGRD : ALBGRI;                                          // func:2393-2401
+  const float U1 = B - C / ALB, U2 = B - C * ALB, U3 = F + C * ALB;
+  const float TMP2 = U1 - AH, TMP3 = U1 + AH;                                             // func:2402-2421
+  // the fast build divides once by each of S1, D1, D2, SIGMA (18 quotients in the reference's form)
+  const float RS1 = 1.0f / S1, RSIG = 1.0f / SIGMA;
+  const float D1 = P1 * TMP2 * RS1 - P2 * TMP3 * S1;
+  const float TMP4 = U2 + AH, TMP5 = U2 - AH;
+  const float D2 = TMP4 * RS1 - TMP5 * S1;
+  const float RD1 = 1.0f / D1, RD2 = 1.0f / D2;
+  const float H1 = -D * P4 - C * F;
+  const float H1S = H1 * RSIG;
+  const float TMP6 = D - H1S * P3;
+  const float TMP7 = (D - C - H1S * (U1 + TMP0)) * S2;
+  const float H2 = (TMP6 * TMP2 * RS1 - P2 * TMP7) * RD1;
+  const float H3 = -(TMP6 * TMP3 * S1 - P1 * TMP7) * RD1;
+  const float H4 = -F * P3 - C * D;
+  const float TMP8 = H4 * RSIG;
+  const float TMP9 = (U3 - TMP8 * (U2 - TMP0)) * S2;
+  const float H5 = -(TMP8 * TMP4 * RS1 + TMP9) * RD2;
+  const float H6 = (TMP8 * TMP5 * S1 + TMP9) * RD2;
+  const float H7 = (C * TMP2) * RD1 * RS1;
+  const float H8 = (-C * TMP3 * S1) * RD1;
+  const float H9 = TMP4 * RD2 * RS1;
+  const float H10 = (-TMP5 * S1) * RD2;
+  if (IC == 0) {                                                                          // func:2426-2450
+    o.FTD = S2 * (1.0f - t.GAP) + t.GAP;
+    o.FTI = (TMP8 * S2 + H5 * S1 + H6 * RS1) * (1.0f - t.GAP);
+    o.FRE = (H1S + H2 + H3) * (1.0f - t.GAP) + ALBGRD * t.GAP;
+    o.FREV = (H1S + H2 + H3) * (1.0f - t.GAP);
+    o.FREG = ALBGRD * t.GAP;
+  } else {
+    o.FTD = 0.0f;
+    o.FTI = (H9 * S1 + H10 * RS1) * (1.0f - t.KOPEN) + t.KOPEN;
+    o.FRE = (H7 + H8) * (1.0f - t.KOPEN) + ALBGRI * t.KOPEN;
+    o.FREV = (H7 + H8) * (1.0f - t.KOPEN) + ALBGRI * t.KOPEN;
+    o.FREG = 0.0f;
+  }
+#else
   const float AH = t.AVMU * H;
   const float P1 = B + AH, P2 = B - AH, P3 = B + TMP0, P4 = B - TMP0;
   const float S1 = m_expf(-H * VAI);
@@ -405,6 +474,7 @@ __device__ __forceinline__ void twostream_band(const TwoStreamCommon& t, int IC,
     o.FREV = (H7 + H8) * (1.0f - t.KOPEN) + ALBGRI * t.KOPEN;
     o.FREG = 0.0f;
   }
+#endif
   o.FAB = 1.0f - o.FRE - (1.0f - ALBGRD) * o.FTD - (1.0f - ALBGRI) * o.FTI;               // func:2454-2455
 }
 
@@ -432,6 +502,27 @@ struct Loop1 {
       mo.CH = mo.CH / UR;
       mo.CM = mo.CM / UR;
     }
+#ifdef NMP_FAST_ALGEBRA
+    // The fast build (tolerance-checked, never bit-compared) merges reciprocals: RAHC is only ever used as 1/RAHC, the
+    // Obukhov-length chain needs one reciprocal, x**0.5 is a square root, and /CWPC, /KH share one reciprocal.
+    RAHC = fmin2(1.0f, mo.CH * UR);                                                       // holds CAH = 1/RAHC in this build
+    float MOZG = 0.0f;
+    if (iter > 1) {
+      float TMP1 = HG * ((KARMAN * GRAV) / (TAH * (RHOAIR * CPAIR)));
+      if (fabsf(TMP1) <= MPE) TMP1 = MPE;
+      MOZG = fmin2((ZPD - Z0MG) * (-TMP1 / cube(mo.FV)), 1.0f);
+    }
+    const float FHGNEW = (MOZG < 0.0f) ? m_powf(1.0f - 15.0f * MOZG, -0.25f) : 1.0f + 4.7f * MOZG;
+    FHG = (iter == 1) ? FHGNEW : 0.5f * (FHG + FHGNEW);
+    const float CWPC = sqrtf(CWP * VAIE * HCAN * FHG);
+    const float RHCAN = 1.0f / HCAN;
+    const float TMP1 = m_expf(-CWPC * Z0MG * RHCAN);
+    const float TMP2 = m_expf(-CWPC * (Z0M + ZPD) * RHCAN);
+    const float KH = fmax2(KARMAN * mo.FV * (HCAN - ZPD), MPE);
+    RAHG = HCAN * m_expf(CWPC) * (TMP1 - TMP2) / (CWPC * KH);
+    const float TMPRB = CWPC * 50.0f / (1.0f - m_expf(-CWPC / 2.0f));
+    RB = TMPRB * rbfac;
+#else
     RAHC = fmax2(1.0f, 1.0f / (mo.CH * UR));                                              // func:2774-2776
     // ragrb, func:3260-3350 (Z0H = Z0M, Z0HG = Z0MG: func:2746-2752)
     float MOZG = 0.0f;
@@ -451,10 +542,57 @@ struct Loop1 {
     RAHG = TMPRAH2 / KH;
     const float TMPRB = CWPC * 50.0f / (1.0f - m_expf(-CWPC / 2.0f));
     RB = TMPRB * rbfac;
+#endif
     const float Tc = tdc(TV);                                                             // func:2787-2795
     esat_sel(Tc, ESTV, DESTV);
   }
 
+#ifdef NMP_FAST_ALGEBRA
+  __device__ __forceinline__ void second(int iter) {
+    CAH = RAHC;                                             // first() left 1/RAHC there            func:2817-2823
+    const float RRB = 1.0f / RB;
+    CVH = 2.0f * VAIE * RRB;
+    const float CGH = 1.0f / RAHG;
+    const float RCOND = 1.0f / (CAH + CVH + CGH);
+    const float ATA = (SFCTMP * CAH + TGV * CGH) * RCOND;
+    const float BTA = CVH * RCOND;
+    const float RHOCP = RHOAIR * CPAIR;
+    const float CSH = (1.0f - BTA) * RHOCP * CVH;
+    const float CAW = CAH;                                                                // func:2826-2834
+    const float CEW = FWET * VAIE * RRB;
+    const float RSUN = RB + RSSUN, RSHA = RB + RSSHA;
+    const float CTW = (1.0f - FWET) * (LAISUNE * RSHA + LAISHAE * RSUN) / (RSUN * RSHA);
+    const float CGW = 1.0f / (RAHG + RSURF);
+    const float RCONDW = 1.0f / (CAW + CEW + CTW + CGW);
+    const float AEA = (EAIR * CAW + ESTG * CGW) * RCONDW;
+    const float BEA = (CEW + CTW) * RCONDW;
+    const float RCG = RHOCP / GAMMAV;
+    const float CEV = (1.0f - BEA) * CEW * RCG;
+    const float CTR = (1.0f - BEA) * CTW * RCG;
+    TAH = ATA + BTA * TV;                                                                 // func:2837-2838
+    EAH = AEA + BEA * ESTV;
+    const float TV3 = cube(TV);
+    IRC = fveg * (AIR + CIR * (TV3 * TV));                                                // func:2840-2848
+    SHC = fveg * RHOCP * CVH * (TV - TAH);
+    EVC = fveg * RCG * CEW * (ESTV - EAH);
+    TR = fveg * RCG * CTW * (ESTV - EAH);
+    if (TV > TFRZ) EVC = fmin2(evcap_liq, EVC);
+    else EVC = fmin2(evcap_ice, EVC);
+    const float B = SAV - IRC - SHC - EVC - TR;                                           // func:2850-2852
+    const float A = fveg * (4.0f * CIR * TV3 + CSH + (CEV + CTR) * DESTV);
+    const float DTV = B / A;
+    IRC = IRC + fveg * 4.0f * CIR * TV3 * DTV;                                            // func:2854-2860
+    SHC = SHC + fveg * CSH * DTV;
+    EVC = EVC + fveg * CEV * DESTV * DTV;
+    TR = TR + fveg * CTR * DESTV * DTV;
+    TV = TV + DTV;
+    H = RHOCP * (TAH - SFCTMP) * CAH;                                                     // func:2864-2868
+    HG = RHOCP * (TGV - TAH) * CGH;
+    iter_done = iter;                                       // QSFC (func:2868) is a function of the final EAH: see qsfc()
+    if (LITER == 1) running = 0;                                                          // func:2870-2875
+    else if (iter >= 5 && fabsf(DTV) <= 0.01f) LITER = 1;
+  }
+#else
   __device__ __forceinline__ void second(int iter) {
     CAH = 1.0f / RAHC;                                                                    // func:2817-2823
     const float RAWC = RAHC, RAWG = RAHG;
@@ -496,6 +634,7 @@ struct Loop1 {
     if (LITER == 1) running = 0;                                                          // func:2870-2875
     else if (iter >= 5 && fabsf(DTV) <= 0.01f) LITER = 1;
   }
+#endif
 };
 // Field lists for the shared-memory hand-off of a column's loop state (member-wise, so the struct itself stays in
 // registers): what a pass only reads, what it carries from pass to pass, and what the caller reads after the last pass.
@@ -1001,6 +1140,9 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   }
 #endif
   if (veg_tile) {
+#ifdef NMP_FAST_ALGEBRA
+    L.QSFC = (0.622f * L.EAH) / (L.SFCPRS - 0.378f * L.EAH);                              // func:2868, of the last pass
+#endif
     r.iter_vege = L.iter_done;
     mo = L.mo; TAH = L.TAH; EAH = L.EAH; TV = L.TV; RAHG = L.RAHG; RAWG = L.RAHG; CAH = L.CAH; CVH = L.CVH;
     IRC = L.IRC; SHC = L.SHC; EVC = L.EVC; TR = L.TR; QSFC = L.QSFC; AIR = L.AIR; CIR = L.CIR;
@@ -1091,6 +1233,15 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
           mb.CH = fmin2(0.01f, mb.CH);
         }
       }
+#ifdef NMP_FAST_ALGEBRA
+      EHB = fmin2(1.0f, mb.CH * UR);                                                      // = 1 / RAHB
+      const float RAWB = 1.0f / EHB;
+      float Tc = tdc(TGB);
+      float DESTG;
+      esat_sel(Tc, ESTGb, DESTG);
+      CSHb = RHOAIR * CPAIR * EHB;
+      CEVb = RHOAIR * CPAIR / (GAMMAG * (RSURF + RAWB));
+#else
       const float RAHB = fmax2(1.0f, 1.0f / (mb.CH * UR));                                // func:3166-3172
       const float RAWB = RAHB;
       EHB = 1.0f / RAHB;
@@ -1099,6 +1250,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       esat_sel(Tc, ESTGb, DESTG);
       CSHb = RHOAIR * CPAIR / RAHB;                                                       // func:3186-3187
       CEVb = RHOAIR * CPAIR / GAMMAG / (RSURF + RAWB);
+#endif
       IRB = CIRb * pow4(TGB) - EMG * f.LWDN;                                              // func:3191-3194
       SHB = CSHb * (TGB - f.SFCTMP);
       EVB = CEVb * (ESTGb * RHSUR - EAIR);

@@ -811,10 +811,15 @@ static_for_rev<NSOIL, 2>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (c.ZWT <= -rc.zsoil[k - 1]) IWT = k - 1;
       });
       const float QDIS = (1.0f - FCRMAX) * 5.0f * m_expf(-T.gen[G_TIMEAN]) * m_expf(-6.0f * (c.ZWT - 2.0f));  // func:6557
+#ifdef NMP_FAST_ALGEBRA   // the fast build keeps this power in fp32, but with libdevice's accurate routine (not the MUFU pair)
+      const float S_NODEf = fmax2(fmin2(1.0f, pick(SMCg, IWT - 1) / SMCMAX), 0.01f);
+      float SMPFZ = -((SP[P_PSISAT] * 1000.0f) * m_accpowf(S_NODEf, -BEXP));
+#else
       double S_NODE = (double)fmin2(1.0f, pick(SMCg, IWT - 1) / SMCMAX);                  // func:6560-6563 (fp64 island)
       const double S_MIN = (double)0.01f;
       S_NODE = S_NODE > S_MIN ? S_NODE : S_MIN;
       float SMPFZ = (float)(-((double)(SP[P_PSISAT] * 1000.0f) * pow(S_NODE, (double)(-BEXP))));
+#endif
       SMPFZ = fmax2(-120000.0f, 0.20f * SMPFZ);
       const float KA = pick(HK, IWT - 1);
       const float znode_iwt = pick(ZNODE, IWT - 1);
