@@ -32,7 +32,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # barriers ncu shows 70-80% of warp samples in stall_no_inst).  Block sizes were swept on B200
 # (profiles/r01_block_sweep.md): the IEEE builds want many warps in lock-step (768 threads, 80 registers,
 # spills absorbed by L1), the smaller fast-math code is best at 2 CTAs x 256 threads, 128 registers.
-COMMON = ["-DNMP_PHASE_BARRIERS"]
+COMMON = ["-DNMP_PHASE_BARRIERS", "-DNMP_PREFETCH_FORCING"]
 VARIANTS = {
     "parity": ("libnoahmp_b200.so", ["-fmad=false", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
     "fast": ("libnoahmp_b200_fast.so", ["--use_fast_math", "-DNMP_FAST_ALGEBRA", "-DNMP_BLOCK=256", "-DNMP_MIN_BLOCKS=3",

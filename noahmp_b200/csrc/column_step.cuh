@@ -25,6 +25,17 @@ struct StepArgs {
   OptRuntime opt;
 };
 
+// Forcing is read once: keep it out of L1, which holds the register spills of the column.
+__device__ __forceinline__ float ld_forcing(const float* p) {
+#ifdef NMP_PREFETCH_FORCING
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -104,9 +115,19 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.S
     Forcing f;
     {
       const float* F = a.forcing + (int64_t)s * a.forcing_stride + ii;
-      f.SFCTMP = __ldg(F + F_SFCTMP * n); f.SFCPRS = __ldg(F + F_SFCPRS * n); f.UU = __ldg(F + F_UU * n);
-      f.VV = __ldg(F + F_VV * n); f.Q2 = __ldg(F + F_Q2 * n); f.SOLDN = __ldg(F + F_SOLDN * n);
-      f.LWDN = __ldg(F + F_LWDN * n); f.PRCP = __ldg(F + F_PRCP * n); f.COSZ = __ldg(F + F_COSZ * n);
+      f.SFCTMP = ld_forcing(F + F_SFCTMP * n); f.SFCPRS = ld_forcing(F + F_SFCPRS * n); f.UU = ld_forcing(F + F_UU * n);
+      f.VV = ld_forcing(F + F_VV * n); f.Q2 = ld_forcing(F + F_Q2 * n); f.SOLDN = ld_forcing(F + F_SOLDN * n);
+      f.LWDN = ld_forcing(F + F_LWDN * n); f.PRCP = ld_forcing(F + F_PRCP * n); f.COSZ = ld_forcing(F + F_COSZ * n);
+#ifdef NMP_PREFETCH_FORCING
+      // the next step's nine forcing lines are asked for now (into L2, no register held), a whole step before the
+      // CTA stops at its first barrier waiting for them
+      if (s + 1 < a.nsteps) {
+        const float* Fn = F + a.forcing_stride;
+static_for<0, NFORCING - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Fn + q * n));
+        });
+      }
+#endif
     }
     const bool last = (s == a.nsteps - 1);
     DiagSink<DIAG> dgs = dg;
@@ -120,7 +141,6 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.S
     const float QAIR = f.Q2;
     const float EAIR = QAIR * f.SFCPRS / (0.622f + 0.378f * QAIR);
     const float RHOAIR = (f.SFCPRS - 0.378f * EAIR) / (RAIR * f.SFCTMP);
-    const float QPRECC = 0.10f * f.PRCP, QPRECL = 0.90f * f.PRCP;
     const float SWDOWN = (f.COSZ <= 0.0f) ? 0.0f : f.SOLDN;
 
     // ---- FICEOLD (driver duty in the reference) and layer thickness, func:322-328 ------
@@ -129,11 +149,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
 
       FICEOLD[IX3(k)] = (k >= c.ISNOW + 1) ? c.SNICE[IX3(k)] / (c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)]) : 0.0f;
     });
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
-      if (k == c.ISNOW + 1) DZSNSO[IX7(k)] = -c.ZSNSO[IX7(k)];
-      else if (k > c.ISNOW + 1) DZSNSO[IX7(k)] = c.ZSNSO[IX7(k > -2 ? k - 1 : k)] - c.ZSNSO[IX7(k)];
-      else DZSNSO[IX7(k)] = 0.0f;
-    });
+    layer_thickness(c, DZSNSO);
     // ---- root-zone temperature and initial water storage, func:332-344 ---------------------------
     float TROOT = 0.0f;
     {
@@ -199,6 +215,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     EnergyResult e;
     energy<Opt, DIAG>(opt, T, rc, c, f, RHOAIR, QAIR, THAIR, EAIR, SWDOWN, IGS, HTOP, elai, esai, fveg, DZSNSO, e, dgs);
     flags |= e.flags;
+    layer_thickness_again(c, DZSNSO);   // energy does not change the layering; not kept alive across it
 
     float soilice[4];
 static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
@@ -212,6 +229,7 @@ static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
   NMP_PHASE_SYNC_AT(1);
     // ---- water ----------------------------------------------------------------------------------------
     WaterResult w;
+    const float QPRECC = 0.10f * f.PRCP, QPRECL = 0.90f * f.PRCP;                                // func:517-518 (atm)
     water<Opt>(opt, T, rc, c, f, e, QPRECC, QPRECL, elai, esai, fveg, QVAP, QDEW, FICEOLD, soilice, DZSNSO, w);
 
   NMP_PHASE_SYNC_AT(2);

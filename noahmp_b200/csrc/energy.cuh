@@ -706,6 +706,22 @@ __device__ __noinline__ void loop1_job(const Opt& opt, float (*xch)[LOOP1_CAP], 
 }
 #endif
 
+// ---- func:322-328  layer thickness from the interface depths ------------------------------------------
+__device__ __forceinline__ void layer_thickness(const Column& c, float (&DZSNSO)[7]) {
+static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    if (k == c.ISNOW + 1) DZSNSO[IX7(k)] = -c.ZSNSO[IX7(k)];
+    else if (k > c.ISNOW + 1) DZSNSO[IX7(k)] = c.ZSNSO[IX7(k > -2 ? k - 1 : k)] - c.ZSNSO[IX7(k)];
+    else DZSNSO[IX7(k)] = 0.0f;
+  });
+}
+// The same seven values again, after a stretch of code that does not use them (the flux solvers): the empty asm makes
+// the depths opaque, so the optimiser cannot merge this with the first evaluation and keep seven registers (or
+// spill slots) alive across the Newton loops.  No instruction is generated for it.
+__device__ __forceinline__ void layer_thickness_again(Column& c, float (&DZSNSO)[7]) {
+static_for<0, 6>([&](auto k_) { constexpr int k = decltype(k_)::value; asm volatile("" : "+f"(c.ZSNSO[k])); });
+  layer_thickness(c, DZSNSO);
+}
+
 // =====================================================================================================
 // energy: func:735-1338 with its callees thermoprop/csnow (1341-1497), radiation/albedo/surrad/snowage/
 // snowalb_*/groundalb (1598-2212), vege_flux (2465-2964), bare_flux (2967-3257), ragrb (3260-3350),
@@ -715,12 +731,14 @@ template <class Opt, bool DIAG>
 __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const RunConst& rc, Column& c,
                                        const Forcing& f, float RHOAIR, float QAIR, float THAIR, float EAIR,
                                        float SWDOWN, float IGS, float HTOP, float elai, float esai, float fveg,
-                                       const float (&DZSNSO)[7], EnergyResult& r, const DiagSink<DIAG>& dg) {
+                                       const float (&DZSNSO_in)[7], EnergyResult& r, const DiagSink<DIAG>& dg) {
   const float* VG = &T.veg[(c.lutyp - 1) * NVEGF];
   const float* SP = &T.soil[(c.sltyp - 1) * NSOILP];
   const int ISURBAN = T.flags[0];
   const float DT = rc.dt;
   const int ISNOW = c.ISNOW;
+  float DZSNSO[7];   // re-derived before tsnosoi (layer_thickness_again), not kept across the flux solvers
+static_for<0, 6>([&](auto k_) { constexpr int k = decltype(k_)::value; DZSNSO[k] = DZSNSO_in[k]; });
   const float SMCMAX = SP[P_SMCMAX], BEXP = SP[P_BEXP], PSISAT = SP[P_PSISAT], SMCWLT = SP[P_SMCWLT];
   const float Z0 = 0.01f, PSIWLT = -150.0f;                                               // func:1017-1018
   r.flags = 0;
@@ -755,36 +773,27 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
 
   NMP_PHASE_SYNC_AT(3);
   // ---- thermoprop, func:1341-1445 (+ csnow 1448-1497, tdfcnd) -----------------------------------
-  float DF[7], HCPCT[7], FACT[7];
+  // Only the top layer's conductivity is needed by the flux solvers (func:1215/1231): the snow layers' and soil layer 1's
+  // (with its interface blend, func:1440-1444) are evaluated here, layers 2-4, the heat capacities and FACT just before
+  // tsnosoi - functions of layer state that nothing touches in between (same values, fewer words alive across the loops).
+  float DF1, DFtop;
+  {
+    float DFS[3];
 static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-    DF[IX7(k)] = 0.0f; HCPCT[IX7(k)] = 0.0f;
-    if (k >= ISNOW + 1) {
-      const float dz = DZSNSO[IX7(k)];
-      const float SNICEV = fmin2(1.0f, c.SNICE[IX3(k)] / (dz * DENICE));                  // func:1476-1478
-      const float epore = 1.0f - SNICEV;
-      const float SNLIQV = fmin2(epore, c.SNLIQ[IX3(k)] / (dz * DENWAT));
-      const float BDSNOI = (c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)]) / dz;                      // func:1482-1490
-      HCPCT[IX7(k)] = CICE * SNICEV + CWAT * SNLIQV;
-      DF[IX7(k)] = 3.2217E-6f * (BDSNOI * BDSNOI);
-    }
-  });
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                      // func:1398-1403
+      DFS[IX3(k)] = 0.0f;
+      if (k >= ISNOW + 1) {
+        const float BDSNOI = (c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)]) / DZSNSO[IX7(k)];        // func:1482-1490
+        DFS[IX3(k)] = 3.2217E-6f * (BDSNOI * BDSNOI);
+      }
+    });
     NMP_PHASE_SYNC_AT(4);
-    const float soilice = c.SMC[IX4(k)] - c.soilwat[IX4(k)];
-    HCPCT[IX7(k)] = c.soilwat[IX4(k)] * CWAT + (1.0f - SMCMAX) * T.gen[G_CSOIL] + (SMCMAX - c.SMC[IX4(k)]) * CPAIR +
-                    soilice * CICE;
-    DF[IX7(k)] = tdfcnd(SMCMAX, SP[P_QUARTZ], c.SMC[IX4(k)], c.soilwat[IX4(k)]);
-    if (c.lutyp == ISURBAN) DF[IX7(k)] = 3.24f;                                           // func:1405-1409
-    if (c.IST == 2) {                                                                     // func:1420-1430
-      if (c.STC[IX7(k)] > TFRZ) { HCPCT[IX7(k)] = CWAT; DF[IX7(k)] = TKWAT; }
-      else { HCPCT[IX7(k)] = CICE; DF[IX7(k)] = TKICE; }
-    }
-  });
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                     // func:1434-1436
-    FACT[IX7(k)] = (k >= ISNOW + 1) ? DT / (HCPCT[IX7(k)] * DZSNSO[IX7(k)]) : 0.0f;
-  });
-  if (ISNOW == 0) DF[IX7(1)] = (DF[IX7(1)] * DZSNSO[IX7(1)] + 0.35f * c.snowh) / (c.snowh + DZSNSO[IX7(1)]);  // func:1440-1444
-  else DF[IX7(1)] = (DF[IX7(1)] * DZSNSO[IX7(1)] + DF[IX7(0)] * DZSNSO[IX7(0)]) / (DZSNSO[IX7(0)] + DZSNSO[IX7(1)]);
+    DF1 = tdfcnd(SMCMAX, SP[P_QUARTZ], c.SMC[0], c.soilwat[0]);                           // func:1398-1403
+    if (c.lutyp == ISURBAN) DF1 = 3.24f;                                                  // func:1405-1409
+    if (c.IST == 2) DF1 = (c.STC[IX7(1)] > TFRZ) ? TKWAT : TKICE;                         // func:1420-1430
+    if (ISNOW == 0) DF1 = (DF1 * DZSNSO[IX7(1)] + 0.35f * c.snowh) / (c.snowh + DZSNSO[IX7(1)]);  // func:1440-1444
+    else DF1 = (DF1 * DZSNSO[IX7(1)] + DFS[IX3(0)] * DZSNSO[IX7(0)]) / (DZSNSO[IX7(0)] + DZSNSO[IX7(1)]);
+    DFtop = (ISNOW == 0) ? DF1 : ((ISNOW == -1) ? DFS[IX3(0)] : ((ISNOW == -2) ? DFS[IX3(-1)] : DFS[IX3(-2)]));
+  }
 
   NMP_PHASE_SYNC_AT(5);
   // ---- radiation, func:1598-1714: albedo (1717-1887) + surrad (1890-2005) ----------------------
@@ -974,7 +983,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   r.LATHEAG = LATHEAG;
 
   const float PSFC = f.SFCPRS;   // offline driver: lowest-model-level pressure == surface pressure
-  const float STCtop = pick(c.STC, IX7(ISNOW + 1)), DFtop = pick(DF, IX7(ISNOW + 1)), DZtop = pick(DZSNSO, IX7(ISNOW + 1));
+  const float STCtop = pick(c.STC, IX7(ISNOW + 1)), DZtop = pick(DZSNSO, IX7(ISNOW + 1));
   const float CO2AIR = rc.co2_frac * f.SFCPRS, O2AIR = rc.o2_frac * f.SFCPRS;
 
   // outputs of the two tiles (zeros of func:1021-1038 for the canopy tile)
@@ -1330,6 +1339,40 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   r.Q2B = Q2B;
 
   NMP_PHASE_SYNC_AT(13);
+  // ---- thermoprop, second half: the remaining conductivities, heat capacities (csnow 1476-1490, func:1398-1403, lakes
+  // 1420-1430) and FACT (1434-1436)
+  layer_thickness_again(c, DZSNSO);
+  float DF[7], HCPCT[7], FACT[7];
+static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    HCPCT[IX7(k)] = 0.0f; DF[IX7(k)] = 0.0f;
+    if (k >= ISNOW + 1) {
+      const float dz = DZSNSO[IX7(k)];
+      const float SNICEV = fmin2(1.0f, c.SNICE[IX3(k)] / (dz * DENICE));                  // func:1476-1478
+      const float epore = 1.0f - SNICEV;
+      const float SNLIQV = fmin2(epore, c.SNLIQ[IX3(k)] / (dz * DENWAT));
+      const float BDSNOI = (c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)]) / dz;                      // func:1482-1490
+      HCPCT[IX7(k)] = CICE * SNICEV + CWAT * SNLIQV;
+      DF[IX7(k)] = 3.2217E-6f * (BDSNOI * BDSNOI);
+    }
+  });
+  DF[IX7(1)] = DF1;
+static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    if (k >= 2) {
+      NMP_PHASE_SYNC_AT(4);
+      DF[IX7(k)] = tdfcnd(SMCMAX, SP[P_QUARTZ], c.SMC[IX4(k)], c.soilwat[IX4(k)]);
+      if (c.lutyp == ISURBAN) DF[IX7(k)] = 3.24f;                                         // func:1405-1409
+    }
+    const float soilice = c.SMC[IX4(k)] - c.soilwat[IX4(k)];
+    HCPCT[IX7(k)] = c.soilwat[IX4(k)] * CWAT + (1.0f - SMCMAX) * T.gen[G_CSOIL] + (SMCMAX - c.SMC[IX4(k)]) * CPAIR +
+                    soilice * CICE;
+    if (c.IST == 2) {                                                                     // func:1420-1430
+      if (c.STC[IX7(k)] > TFRZ) { HCPCT[IX7(k)] = CWAT; if (k >= 2) DF[IX7(k)] = TKWAT; }
+      else { HCPCT[IX7(k)] = CICE; if (k >= 2) DF[IX7(k)] = TKICE; }
+    }
+  });
+static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    FACT[IX7(k)] = (k >= ISNOW + 1) ? DT / (HCPCT[IX7(k)] * DZSNSO[IX7(k)]) : 0.0f;
+  });
   // ---- tsnosoi: hrt + hstep + rosr12, func:3987-4288 ---------------------------------------------
   {
     const float ZBOTSNO = T.gen[G_ZBOT] - c.snowh;                                        // func:4039
