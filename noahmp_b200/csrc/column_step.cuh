@@ -51,7 +51,11 @@ template <class Opt, bool EXT, bool DIAG, bool BUDGET>
 #ifndef NMP_MIN_BLOCKS
 #define NMP_MIN_BLOCKS 2
 #endif
+#if NMP_MIN_BLOCKS > 0
 __global__ void __launch_bounds__(NMP_BLOCK, NMP_MIN_BLOCKS) column_step_kernel(const StepArgs a) {
+#else   // explicit register budget (tuning builds): -DNMP_MIN_BLOCKS=0 -DNMP_MAXNREG=n
+__global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
+#endif
   __shared__ Tables T;
   {  // stage the parameter tables (about 9.5 KB) into shared memory, coalesced
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables);

@@ -109,15 +109,21 @@ def main():
     base = int(rows[0]["Address"], 16)
     here = os.path.dirname(os.path.abspath(__file__))
     ptab = phase_table(csrc or os.path.join(here, "..", "noahmp_b200", "csrc"))
-    by_line, by_phase, by_leaf = (defaultdict(lambda: [0, 0, 0]) for _ in range(3))
-    tot = [0, 0, 0]
+    NV = 9   # instr, thread-instr, samples, stall_long_sb, stall_barrier, stall_wait, stall_short_sb, local loads, local stores
+    by_line, by_phase, by_leaf = (defaultdict(lambda: [0] * NV) for _ in range(3))
+    tot = [0] * NV
     mism = 0
     for r in rows:
         off = int(r["Address"], 16) - base
         chain, text = sass.get(off, ((), ""))
         if text.split()[:1] != r["Source"].split()[:1] and not (text.startswith("@") or r["Source"].strip().startswith("@")):
             mism += 1
-        v = (int(r["Instructions Executed"]), int(r["Thread Instructions Executed"]), int(r["# Samples"]))
+        op = r["Source"].replace("@", " ").split()
+        op = next((o for o in op if not o.startswith(("P", "!P", "UP", "!UP"))), "")
+        nexe = int(r["Instructions Executed"])
+        v = (nexe, int(r["Thread Instructions Executed"]), int(r["# Samples"]), int(r.get("stall_long_sb", 0) or 0),
+             int(r.get("stall_barrier", 0) or 0), int(r.get("stall_wait", 0) or 0), int(r.get("stall_short_sb", 0) or 0),
+             nexe if op.startswith("LDL") else 0, nexe if op.startswith("STL") else 0)
         body = [c for c in chain if c[0] != "common.cuh"] or list(chain)      # skip the libm / static_for wrappers
         loc = body[0] if body else None                                         # innermost physics line
         leaf = ptab.get(loc, loc[0] if loc else "?")
@@ -126,18 +132,21 @@ def main():
         # one "inlined at" record, so an outermost-frame rule files phasechange under the snow compaction loop.
         ph = next((ptab[c] for c in body if c in ptab and (":" in ptab[c] or ptab[c] == "column_step")), leaf)
         for acc in (by_line[loc], by_phase[ph], by_leaf[leaf], tot):
-            for i in range(3):
+            for i in range(NV):
                 acc[i] += v[i]
     if mism > len(rows) // 50:
         print(f"WARNING: {mism} of {len(rows)} instructions do not match the library's SASS - different build?")
     print(f"total warp-instructions {tot[0]:.4g}, lanes/instr {tot[1] / max(tot[0], 1):.2f}, samples {tot[2]}")
     for title, tab in (("phase of the step (callees included)", by_phase),
                        ("routine (innermost frame)", by_leaf)):
-        print(f"\n| {title} | warp-instr % | lanes active | stall samples % |\n|---|---|---|---|")
+        print(f"\n| {title} | warp-instr % | lanes active | stall samples % | long_sb % | barrier % | wait % | short_sb % | "
+              f"local ld+st % of its instr |\n|---|---|---|---|---|---|---|---|---|")
         for ph, v in sorted(tab.items(), key=lambda kv: -kv[1][0]):
             if v[0] * 1000 < tot[0]:
                 continue
-            print(f"| {ph} | {100 * v[0] / tot[0]:.1f} | {v[1] / max(v[0], 1):.1f} | {100 * v[2] / max(tot[2], 1):.1f} |")
+            print(f"| {ph} | {100 * v[0] / tot[0]:.1f} | {v[1] / max(v[0], 1):.1f} | {100 * v[2] / max(tot[2], 1):.1f} | "
+                  f"{100 * v[3] / max(tot[2], 1):.1f} | {100 * v[4] / max(tot[2], 1):.1f} | {100 * v[5] / max(tot[2], 1):.1f} | "
+                  f"{100 * v[6] / max(tot[2], 1):.1f} | {100 * (v[7] + v[8]) / max(v[0], 1):.1f} |")
     print(f"\ntop {top} source lines\n| file:line | warp-instr % | lanes | samples % |\n|---|---|---|---|")
     for loc, v in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:
         print(f"| {loc[0]}:{loc[1]} | {100 * v[0] / tot[0]:.2f} | {v[1] / max(v[0], 1):.1f} | {100 * v[2] / max(tot[2], 1):.2f} |" if loc else f"| ? | {100 * v[0] / tot[0]:.2f} | | |")
