@@ -30,13 +30,13 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # All variants are the SAME source.  NMP_PHASE_BARRIERS puts a CTA barrier at every phase boundary so the warps
 # of a CTA stay inside one instruction-cache window (the step is ~16k SASS instructions; without the
 # barriers ncu shows 70-80% of warp samples in stall_no_inst).  Block sizes were swept on B200
-# (profiles/r01_block_sweep.md): the IEEE builds want many warps in lock-step (768 threads, 80 registers,
-# spills absorbed by L1), the smaller fast-math code is best at 2 CTAs x 256 threads, 128 registers.
-COMMON = ["-DNMP_PHASE_BARRIERS", "-DNMP_PREFETCH_FORCING"]
+# (profiles/r01_block_sweep.md, r01_tuning.md): the IEEE builds (3x the code) want many warps in lock-step (768 threads,
+# 80 registers; 256 x 3 is 37 % slower there), the smaller fast-math code is best at 3 CTAs x 256 threads, 80 registers.
+# NMP_SYNC_MASK=0x7f7af: every numbered barrier site except the three inside fixed-count loops (4, 6, 11), +2 %.
+COMMON = ["-DNMP_PHASE_BARRIERS", "-DNMP_PREFETCH_FORCING", "-DNMP_SYNC_MASK=0x7f7afu"]
 VARIANTS = {
     "parity": ("libnoahmp_b200.so", ["-fmad=false", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
-    "fast": ("libnoahmp_b200_fast.so", ["--use_fast_math", "-DNMP_FAST_ALGEBRA", "-DNMP_BLOCK=256", "-DNMP_MIN_BLOCKS=3",
-                                        "-DNMP_SYNC_MASK=0x7f7afu"]),
+    "fast": ("libnoahmp_b200_fast.so", ["--use_fast_math", "-DNMP_FAST_ALGEBRA", "-DNMP_BLOCK=256", "-DNMP_MIN_BLOCKS=3"]),
     "strict": ("libnoahmp_b200_strict.so", ["-fmad=false", "-DNMP_CR_LIBM", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
 }
 
