@@ -117,6 +117,23 @@ def ncu_traffic(nloc, nsteps, variant):
     return None
 
 
+def issue_roofline(cell_steps_per_s, variant, sm_count, sm_mhz):
+    """The bound the kernel actually runs against: one warp-instruction per scheduler per clock (4 schedulers per SM).
+    Warp-instructions per cell-step come from the committed ncu capture of this workload (profiles/r01_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            t = json.load(fh)
+        if t["variant"] != variant or not sm_mhz:
+            return None
+        per = t["warp_inst"] / (t["columns"] * t["model_steps"])
+        peak = sm_count * 4 * sm_mhz * 1e6
+        return {"bound": "issue", "warp_inst_per_cell_step": per, "achieved": cell_steps_per_s * per, "peak": peak,
+                "unit": "warp-inst/s", "frac": cell_steps_per_s * per / peak,
+                "source": "instruction count of profiles/r01_traffic.json (ncu), SM clock sampled during the timed region"}
+    except Exception:
+        return None
+
+
 def build_workload(args):
     w = synth.make_workload(args.workload, ncol=args.ncol, nsteps=args.model_steps)
     if not args.no_sort_columns:
@@ -457,6 +474,9 @@ def run_ours(args):
                              "note": "kernel is instruction-issue bound (see profiles/); fraction is reported against HBM as "
                                      "the contract asks"},
                 "e2e": e2e, "e2e_state_roundtrip": e2e_rt, "other_variants": other, "aux_kernels": aux, "gpu_launches": int(launches), "clocks": clocks, "budget": bud}
+        line["roofline_issue"] = issue_roofline(nloc * w.nsteps / (k_ms * 1e-3), args.variant,
+                                                torch.cuda.get_device_properties(dev).multi_processor_count,
+                                                (clocks or {}).get("sm_mhz"))
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_sample_cols)
             tr = translated_reference_leg(w)

@@ -3,8 +3,9 @@ namelist describes (offline/noahmp_config.py:77-102, run/case.nml) but nothing i
 (SURVEY 8f ranks 1-3).  Host logic only; the column physics and the forcing preparation run on the GPU.
 
 Two modes:
-* file driven  -- ``initialization_file`` is an ``.npz`` of columns (see :func:`columns_from_init`) and
-  ``input_directory`` holds forcing records (``forcing.py``); outputs and restarts are written as ``.npz``.
+* file driven  -- ``initialization_file`` is an ``.npz`` of columns or a NetCDF-3 file (see :func:`columns_from_init`,
+  ``ncio.py``) and ``input_directory`` holds forcing records (``forcing.py``); outputs and restarts are written in the
+  format of the initialisation file (``.npz``, or ``*.LDASOUT_DOMAIN1`` / ``RESTART.*_DOMAIN1`` netCDF on its grid).
 * synthetic    -- no initialization file: the single-point workload of ``synth.py`` over the namelist period
   (BASELINE.json configs[0]).
 """
@@ -17,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import forcing as F
-from . import layout as L, synth
+from . import layout as L, ncio, synth
 from .engine import NoahMP
 from .tables import ParamTables
 
@@ -31,6 +32,7 @@ class Columns:
     static_i: np.ndarray   # [ncol]
     lat: np.ndarray        # radians
     lon: np.ndarray        # radians
+    grid: tuple = ()       # (south_north, west_east) of a netCDF initialisation file; () for flat column lists
 
     @property
     def ncol(self) -> int:
@@ -83,8 +85,9 @@ def snow_layers_from_depth(snowh, sneqv, tsnow, zsoil=synth.ZSOIL):
 
 def columns_from_init(path: str, tables: ParamTables) -> Columns:
     """``.npz`` keys: lat, lon [deg]; lutyp, sltyp, slptyp, isc (ints); shdfac, tbot; tsk (skin T), stc[4], smc[4],
-    optional sh2o[4], snowh [m], sneqv [mm], canliq, zwt, wa."""
-    z = np.load(path)
+    optional sh2o[4], snowh [m], sneqv [mm], canliq, zwt, wa.  A NetCDF-3 file with the HRLDAS / WRF variable names
+    (``ncio.INIT_ALIASES``) is accepted as well; its grid is flattened row-major."""
+    z = ncio.read_init(path) if ncio.is_netcdf(path) else np.load(path)
     n = z["lat"].size
     st = synth._blank_state(n)
     sl = z["sltyp"].astype(np.int64)
@@ -135,7 +138,7 @@ def columns_from_init(path: str, tables: ParamTables) -> Columns:
     ice = np.where(lut == tables.flags["ISICE"], 1, 0)            # ICE: 1 land ice (func:116)
     si = L.pack_types(lut, sl, z["slptyp"].astype(np.int64) if "slptyp" in z.files else ones,
                       z["isc"].astype(np.int64) if "isc" in z.files else 4 * ones, ist, ice).astype(np.int32)
-    return Columns(st, sf, si, lat, lon)
+    return Columns(st, sf, si, lat, lon, tuple(getattr(z, "grid", ())))
 
 
 def write_restart(path: str, state: np.ndarray, when: dt.datetime, step: int) -> None:
@@ -144,6 +147,8 @@ def write_restart(path: str, state: np.ndarray, when: dt.datetime, step: int) ->
 
 
 def read_restart(path: str):
+    if ncio.is_netcdf(path):
+        return ncio.read_restart(path)
     z = np.load(path)
     if list(z["planes"]) != L.STATE:
         raise ValueError(f"{path}: state plane list does not match this build")
@@ -158,6 +163,7 @@ def run_files(cfg, device: int = 0, variant="fast", max_steps_per_launch: int = 
     tables = (ParamTables.from_tbl_dir(cfg.table_directory, cfg.soil_table_tag, cfg.veg_table_tag)
               if getattr(cfg, "table_directory", None) else ParamTables.default(cfg.soil_table_tag, cfg.veg_table_tag))
     cols = columns_from_init(cfg.initfile, tables)
+    as_nc = ncio.is_netcdf(cfg.initfile)    # outputs and restarts follow the format of the initialisation file
     t, step0 = cfg.begdatetime, 0
     res_path = cfg.resfile if os.path.isabs(str(cfg.resfile)) else os.path.join(cfg.resdir, str(cfg.resfile))
     if os.path.isfile(res_path):
@@ -189,12 +195,20 @@ def run_files(cfg, device: int = 0, variant="fast", max_steps_per_launch: int = 
         nsteps += g
         if F.is_boundary(t, cfg.begdatetime, out_freq):
             os.makedirs(cfg.outdir, exist_ok=True)
-            p = os.path.join(cfg.outdir, F.stamp(t) + ".LDASOUT.npz")
-            np.savez(p, diag=diag.cpu().numpy(), planes=np.asarray(L.DIAG), time=F.stamp(t))
+            if as_nc:
+                p = os.path.join(cfg.outdir, F.stamp(t) + ".LDASOUT_DOMAIN1")
+                ncio.write_output(p, diag.cpu().numpy(), t, cols.grid)
+            else:
+                p = os.path.join(cfg.outdir, F.stamp(t) + ".LDASOUT.npz")
+                np.savez(p, diag=diag.cpu().numpy(), planes=np.asarray(L.DIAG), time=F.stamp(t))
             written.append(p)
         if F.is_boundary(t, cfg.begdatetime, res_freq):
-            p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + ".npz")
-            write_restart(p, state.cpu().numpy(), t, nsteps)
+            if as_nc:
+                p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + "_DOMAIN1")
+                ncio.write_restart(p, state.cpu().numpy(), t, nsteps, cols.grid)
+            else:
+                p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + ".npz")
+                write_restart(p, state.cpu().numpy(), t, nsteps)
             written.append(p)
     torch.cuda.synchronize()
     out = _summary(state.cpu().numpy(), diag.cpu().numpy(), budget.cpu().numpy(), ncol, nsteps, dtm.total_seconds(),

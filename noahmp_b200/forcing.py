@@ -4,7 +4,8 @@ implements (it only carries the config fields, offline/noahmp_config.py:81-86,98
 
 Host side here = file I/O and the handful of per-step scalars; the per-column arithmetic runs on the GPU
 (``noahmp_prepare_forcing``).  Record files: ``<input_directory>/<YYYYMMDDHHMM>.npy``, float32 ``[8][ncol]`` in
-the order SFCTMP SFCPRS UU VV Q2 SOLDN LWDN PRCP (netCDF is not available in this image)."""
+the order SFCTMP SFCPRS UU VV Q2 SOLDN LWDN PRCP, or NetCDF-3 records ``<YYYYMMDDHH>.LDASIN_DOMAIN1`` /
+``<YYYYMMDDHHMM>.nc`` with the HRLDAS variable names (``ncio.py``)."""
 from __future__ import annotations
 
 import calendar
@@ -92,7 +93,12 @@ class RecordReader:
         self._cache: dict = {}
 
     def path(self, t: dt.datetime) -> str:
-        return os.path.join(self.dir, stamp(t) + ".npy")
+        """The record of time ``t``: ``.npy`` first, then the netCDF names; the ``.npy`` name when none exists."""
+        names = [stamp(t) + ".npy", stamp(t) + ".nc", t.strftime("%Y%m%d%H") + ".LDASIN_DOMAIN1", stamp(t) + ".LDASIN_DOMAIN1"]
+        for n in names:
+            if os.path.isfile(os.path.join(self.dir, n)):
+                return os.path.join(self.dir, n)
+        return os.path.join(self.dir, names[0])
 
     def bracket(self, t: dt.datetime):
         """(t0, t1, weight) with t0 <= t < t1 on the record grid."""
@@ -109,7 +115,11 @@ class RecordReader:
             p = self.path(t)
             if not os.path.isfile(p):
                 raise FileNotFoundError(f"ERR: Unable to find forcing record {p}")
-            a = np.load(p)
+            if p.endswith(".npy"):
+                a = np.load(p)
+            else:
+                from . import ncio
+                a = ncio.read_record(p, self.ncol)
             if a.shape != (len(RECORD_VARS), self.ncol) or a.dtype != np.float32:
                 raise ValueError(f"{p}: expected float32 [{len(RECORD_VARS)}][{self.ncol}], got {a.dtype} {a.shape}")
             if len(self._cache) >= 2:

@@ -2,6 +2,7 @@
 snow layering, restart files, and the numpy statement of the forcing-preparation kernel."""
 import datetime as dt
 import math
+import os
 
 import numpy as np
 import pytest
@@ -78,3 +79,108 @@ def test_restart_round_trip(tmp_path):
     write_restart(p, st, dt.datetime(2000, 1, 1, 3), 12)
     st2, when, step = read_restart(p)
     assert np.array_equal(st.view(np.int32), st2.view(np.int32)) and when == dt.datetime(2000, 1, 1, 3) and step == 12
+
+
+# ---- NetCDF-3 input / output (noahmp_b200/ncio.py) ------------------------------------------------------------------
+def _write_wrf_style_init(path, init, grid):
+    """The same columns as a WRF-style file: [Time, south_north, west_east], soil [Time, soil_layers_stag, sn, we],
+    vegetation fraction in percent."""
+    from scipy.io import netcdf_file
+    ny, nx = grid
+    with netcdf_file(path, "w", version=2) as nc:
+        nc.createDimension("Time", 1)
+        nc.createDimension("soil_layers_stag", 4)
+        nc.createDimension("south_north", ny)
+        nc.createDimension("west_east", nx)
+        two = ("Time", "south_north", "west_east")
+        for name, key, typ in (("XLAT", "lat", "f4"), ("XLONG", "lon", "f4"), ("IVGTYP", "lutyp", "i4"), ("ISLTYP", "sltyp", "i4"),
+                               ("SLOPETYP", "slptyp", "i4"), ("ISC", "isc", "i4"), ("TMN", "tbot", "f4"), ("TSK", "tsk", "f4"),
+                               ("SNOWH", "snowh", "f4"), ("SNOW", "sneqv", "f4")):
+            v = nc.createVariable(name, typ, two)
+            v[:] = np.asarray(init[key]).astype(typ).reshape(1, ny, nx)
+        v = nc.createVariable("VEGFRA", "f4", two)
+        v[:] = (np.asarray(init["shdfac"], np.float32) * np.float32(100.0)).reshape(1, ny, nx)
+        for name, key in (("TSLB", "stc"), ("SMOIS", "smc")):
+            v = nc.createVariable(name, "f4", ("Time", "soil_layers_stag", "south_north", "west_east"))
+            v[:] = np.asarray(init[key], np.float32).reshape(1, 4, ny, nx)
+
+
+def _init_dict(ncol):
+    from noahmp_b200 import synth
+    w = synth.make_workload("global025", ncol=ncol, nsteps=1)
+    rng = np.random.default_rng(3)
+    lat = np.degrees(w.static_f[L.C["LAT"]].astype(np.float64)).astype(np.float32)
+    # shdfac as k/128: survives the percent round trip of VEGFRA exactly
+    shd = (np.round(w.static_f[L.C["SHDFAC"]] * 128.0) / 128.0).astype(np.float32)
+    return dict(lat=lat, lon=rng.uniform(-120, 40, ncol).astype(np.float32), lutyp=w.static_i & 0xff, sltyp=(w.static_i >> 8) & 0xff,
+                slptyp=(w.static_i >> 16) & 0xff, isc=(w.static_i >> 24) & 0xf, shdfac=shd,
+                tbot=w.static_f[L.C["TBOT"]], tsk=w.state[L.S["TG"]], stc=np.stack([w.state[L.stc(k)] for k in range(1, 5)]),
+                smc=np.stack([w.state[L.smc(k)] for k in range(1, 5)]), snowh=np.where(lat > 55, 0.3, 0.0).astype(np.float32),
+                sneqv=np.where(lat > 55, 75.0, 0.0).astype(np.float32))
+
+
+def test_netcdf_init_gives_the_same_columns_as_npz(tmp_path, tables):
+    from noahmp_b200 import ncio
+    from noahmp_b200.driver import columns_from_init
+    init = _init_dict(96)
+    np.savez(tmp_path / "init.npz", **init)
+    _write_wrf_style_init(str(tmp_path / "init.nc"), init, (8, 12))
+    assert ncio.is_netcdf(str(tmp_path / "init.nc")) and not ncio.is_netcdf(str(tmp_path / "init.npz"))
+    a = columns_from_init(str(tmp_path / "init.npz"), tables)
+    b = columns_from_init(str(tmp_path / "init.nc"), tables)
+    assert b.grid == (8, 12) and a.grid == ()
+    assert np.array_equal(a.state.view(np.int32), b.state.view(np.int32))
+    assert np.array_equal(a.static_f.view(np.int32), b.static_f.view(np.int32)) and np.array_equal(a.static_i, b.static_i)
+    assert np.array_equal(a.lon, b.lon)
+
+
+def test_netcdf_forcing_record_and_name_lookup(tmp_path):
+    from scipy.io import netcdf_file
+    rng = np.random.default_rng(5)
+    rec = rng.normal(280.0, 20.0, size=(8, 24)).astype(np.float32)
+    t = dt.datetime(2000, 7, 1, 3)
+    with netcdf_file(str(tmp_path / "2000070103.LDASIN_DOMAIN1"), "w", version=2) as nc:
+        nc.createDimension("Time", 1)
+        nc.createDimension("south_north", 4)
+        nc.createDimension("west_east", 6)
+        for i, name in enumerate(("T2D", "PSFC", "U2D", "V2D", "Q2D", "SWDOWN", "LWDOWN", "RAINRATE")):
+            v = nc.createVariable(name, "f4", ("Time", "south_north", "west_east"))
+            v[:] = rec[i].reshape(1, 4, 6)
+    rd = F.RecordReader(str(tmp_path), "1 hour", dt.datetime(2000, 7, 1), 24, "cpu")
+    assert rd.path(t).endswith("2000070103.LDASIN_DOMAIN1")
+    assert np.array_equal(rd.record(t).numpy().view(np.int32), rec.view(np.int32))
+    with pytest.raises(FileNotFoundError):
+        rd.record(dt.datetime(2000, 7, 1, 4))
+    with pytest.raises(ValueError):                            # a run with another column count must not read this record
+        F.RecordReader(str(tmp_path), "1 hour", dt.datetime(2000, 7, 1), 25, "cpu").record(t)
+    np.save(tmp_path / "200007010300.npy", rec + 1)            # a .npy record of the same hour takes precedence
+    assert F.RecordReader(str(tmp_path), "1 hour", dt.datetime(2000, 7, 1), 24, "cpu").path(t).endswith(".npy")
+
+
+def test_netcdf_restart_and_output_round_trip(tmp_path):
+    from noahmp_b200 import ncio
+    rng = np.random.default_rng(7)
+    st = rng.normal(size=(L.NSTATE, 12)).astype(np.float32)
+    st[L.S["ISNOW"]] = np.array([0, -1, -2, -3] * 3, np.int32).view(np.float32)
+    st[L.S["TV"], 3] = np.float32("nan")                       # bit patterns survive, NaN included
+    p = str(tmp_path / "r" / "RESTART.200001010300_DOMAIN1")
+    ncio.write_restart(p, st, dt.datetime(2000, 1, 1, 3), 12, grid=(3, 4))
+    st2, when, step = read_restart(p)                           # the driver's reader recognises the format
+    assert np.array_equal(st.view(np.int32), st2.view(np.int32)) and when == dt.datetime(2000, 1, 1, 3) and step == 12
+    dg = rng.normal(size=(L.NDIAG, 12)).astype(np.float32)
+    dg[L.D["ITER"]] = np.arange(12, dtype=np.int32).view(np.float32)
+    q = str(tmp_path / "o" / "200001010300.LDASOUT_DOMAIN1")
+    ncio.write_output(q, dg, dt.datetime(2000, 1, 1, 3), grid=())          # flat column list: one 'ncol' dimension
+    back, when, _ = ncio.read_planes(q, L.DIAG, int_planes=("ITER", "FLAGS"))
+    assert np.array_equal(back.view(np.int32)[:-1], dg.view(np.int32)[:-1]) and when == dt.datetime(2000, 1, 1, 3)
+    from scipy.io import netcdf_file
+    with netcdf_file(p, "r", mmap=False) as nc:                 # readable by any netCDF-3 tool: named grid dimensions
+        assert nc.variables["STCp1"].dimensions == ("Time", "south_north", "west_east") and nc.variables["ISNOW"].data.dtype.kind == "i"
+
+
+def test_netcdf4_files_are_refused_with_a_hint(tmp_path):
+    from noahmp_b200 import ncio
+    p = tmp_path / "init4.nc"
+    p.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(ValueError, match="nccopy -k classic"):
+        ncio.is_netcdf(str(p))

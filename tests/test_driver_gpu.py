@@ -86,6 +86,47 @@ def test_file_driven_run_outputs_and_restart_continuity(tmp_path, tables):
     assert (isn < 0).any() and (isn == 0).any()
 
 
+def test_netcdf_driven_run_equals_the_npz_driven_run(tmp_path, tables):
+    """The same case with a WRF-style netCDF-3 initialisation file and LDASIN records: identical state, netCDF outputs."""
+    from scipy.io import netcdf_file
+    from test_driver import _write_wrf_style_init
+    from noahmp_b200 import ncio
+    from noahmp_b200.driver import read_restart, run_files
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    cfg = _make_case(tmp_path / "a", hours=4)
+    init = dict(np.load(tmp_path / "a" / "init.npz"))
+    # WRF files carry the vegetation fraction as a percentage: use fractions k/128, which survive x100 /100 in fp32 exactly
+    init["shdfac"] = (np.round(init["shdfac"] * 128.0) / 128.0).astype(np.float32)
+    init["lat"], init["lon"] = init["lat"].astype(np.float32), init["lon"].astype(np.float32)   # XLAT / XLONG are float32
+    np.savez(tmp_path / "a" / "init.npz", **init)
+    ref = run_files(cfg, variant="parity")
+    ref_state, _, _ = read_restart(str(tmp_path / "a" / "restart" / "RESTART.200007010200.npz"))
+    # the netCDF twin: init on an 8 x 12 grid, records as <YYYYMMDDHH>.LDASIN_DOMAIN1
+    _write_wrf_style_init(str(tmp_path / "b" / "init.nc"), init, (8, 12))
+    os.makedirs(tmp_path / "b" / "ldasin")
+    for f in sorted(os.listdir(tmp_path / "a" / "ldasin")):
+        rec = np.load(tmp_path / "a" / "ldasin" / f)
+        with netcdf_file(str(tmp_path / "b" / "ldasin" / (f[:10] + ".LDASIN_DOMAIN1")), "w", version=2) as nc:
+            nc.createDimension("Time", 1)
+            nc.createDimension("south_north", 8)
+            nc.createDimension("west_east", 12)
+            for i, name in enumerate(("T2D", "PSFC", "U2D", "V2D", "Q2D", "SWDOWN", "LWDOWN", "RAINRATE")):
+                v = nc.createVariable(name, "f4", ("Time", "south_north", "west_east"))
+                v[:] = rec[i].reshape(1, 8, 12)
+    cfg.initfile = str(tmp_path / "b" / "init.nc")
+    cfg.indir, cfg.outdir, cfg.resdir = (str(tmp_path / "b" / d) for d in ("ldasin", "out", "restart"))
+    got = run_files(cfg, variant="parity")
+    assert got["steps"] == ref["steps"] == 16 and got["flagged_column_launches"] == 0
+    names = sorted(os.path.basename(p) for p in got["files_written"])
+    assert names == ["200007010100.LDASOUT_DOMAIN1", "RESTART.200007010000_DOMAIN1", "RESTART.200007010200_DOMAIN1"]
+    st, when, step = read_restart(str(tmp_path / "b" / "restart" / "RESTART.200007010200_DOMAIN1"))
+    assert when == dt.datetime(2000, 7, 1, 2) and step == 16
+    assert np.array_equal(st.view(np.int32), ref_state.view(np.int32))
+    out, _, _ = ncio.read_planes(str(tmp_path / "b" / "out" / "200007010100.LDASOUT_DOMAIN1"), L.DIAG, int_planes=("ITER", "FLAGS"))
+    assert np.isfinite(out[L.D["TRAD"]]).all()
+
+
 def test_main_entry_point_runs_the_synthetic_single_point(tmp_path):
     import importlib.util
     from conftest import ROOT
