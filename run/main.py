@@ -4,8 +4,10 @@
 default ``case.nml``, ``main(nmlfile)``), but instead of printing ``dir(cfg)`` (main:12-14) it loads the
 parameter tables, builds the columns and advances them on the GPU through the C ABI.
 
-The reference defines no forcing reader, no ``init.nc`` reader and no cosine-zenith computation,
-so this driver runs the synthetic single-point workload of ``noahmp_b200.synth`` over the namelist's period.
+The reference defines no forcing reader, no ``init.nc`` reader and no cosine-zenith computation.  When the
+namelist's ``initialization_file`` exists (NetCDF-3 with WRF/HRLDAS names, or ``.npz``) the file-driven loop of
+``noahmp_b200.driver.run_files`` runs: forcing records from ``input_directory``, outputs and restarts at the namelist's
+frequencies.  Otherwise the synthetic single-point workload of ``noahmp_b200.synth`` is run over the namelist's period.
 """
 import argparse
 import os
