@@ -79,9 +79,9 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
     c.CANLIQ = S[S_CANLIQ * n]; c.CANICE = S[S_CANICE * n]; c.TV = S[S_TV * n]; c.TG = S[S_TG * n];
     c.QSNOW = S[S_QSNOW * n]; c.ISNOW = __float_as_int(S[S_ISNOW * n]); c.snowh = S[S_SNOWH * n];
     c.sneqv = S[S_SNEQV * n]; c.ZWT = S[S_ZWT * n]; c.WA = S[S_WA * n]; c.WT = S[S_WT * n]; c.TAUSS = S[S_TAUSS * n];
-static_for<0, (7) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.STC[k] = S[(S_STC + k) * n]; c.ZSNSO[k] = S[(S_ZSNSO + k) * n]; });
-static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.soilwat[k] = S[(S_SOILWAT + k) * n]; c.SMC[k] = S[(S_SMC + k) * n]; });
-static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.SNICE[k] = S[(S_SNICE + k) * n]; c.SNLIQ[k] = S[(S_SNLIQ + k) * n]; });
+    static_for<0, (7) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.STC[k] = S[(S_STC + k) * n]; c.ZSNSO[k] = S[(S_ZSNSO + k) * n]; });
+    static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.soilwat[k] = S[(S_SOILWAT + k) * n]; c.SMC[k] = S[(S_SMC + k) * n]; });
+    static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.SNICE[k] = S[(S_SNICE + k) * n]; c.SNLIQ[k] = S[(S_SNLIQ + k) * n]; });
     if (EXT) {
       c.QSFC = S[S_QSFC * n]; c.TAH = S[S_TAH * n]; c.CM = S[S_CM * n]; c.CH = S[S_CH * n]; c.WSLAKE = S[S_WSLAKE * n];
       c.LFMASS = S[S_LFMASS * n]; c.RTMASS = S[S_RTMASS * n]; c.STMASS = S[S_STMASS * n]; c.WOOD = S[S_WOOD * n];
@@ -127,7 +127,7 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; c.S
       // CTA stops at its first barrier waiting for them
       if (s + 1 < a.nsteps) {
         const float* Fn = F + a.forcing_stride;
-static_for<0, NFORCING - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
+        static_for<0, NFORCING - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(Fn + q * n));
         });
       }
@@ -149,8 +149,7 @@ static_for<0, NFORCING - 1>([&](auto q_) { constexpr int q = decltype(q_)::value
 
     // ---- FICEOLD (driver duty in the reference) and layer thickness, func:322-328 ------
     float FICEOLD[3], DZSNSO[7];
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+    static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
       FICEOLD[IX3(k)] = (k >= c.ISNOW + 1) ? c.SNICE[IX3(k)] / (c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)]) : 0.0f;
     });
     layer_thickness(c, DZSNSO);
@@ -158,16 +157,15 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     float TROOT = 0.0f;
     {
       const float zroot = -pick(rc.zsoil, NROOT - 1);
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k <= NROOT) TROOT = TROOT + c.STC[IX7(k)] * DZSNSO[IX7(k)] / zroot;
       });
     }
     float BEG_WB = 0.0f;
     if (c.IST == 1) {
       BEG_WB = c.CANLIQ + c.CANICE + c.sneqv + c.WA;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- BEG_WB = BEG_WB + c.SMC[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        BEG_WB = BEG_WB + c.SMC[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
       });
     }
     // ---- phenology, func:534-630 --------------------------------------------------------------------
@@ -222,8 +220,8 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     layer_thickness_again(c, DZSNSO);   // energy does not change the layering; not kept alive across it
 
     float soilice[4];
-static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
- soilice[k] = fmax2(0.0f, c.SMC[k] - c.soilwat[k]);
+    static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      soilice[k] = fmax2(0.0f, c.SMC[k] - c.soilwat[k]);
     });            // func:414
     c.SNEQVO = c.sneqv;                                                                        // func:415
     const float QVAP = fmax2(e.FGEV / e.LATHEAG, 0.0f);                                        // func:417-419
@@ -251,8 +249,8 @@ static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
     float ERRWAT = 0.0f;
     if (c.IST == 1) {
       float END_WB = c.CANLIQ + c.CANICE + c.sneqv + c.WA;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- END_WB = END_WB + c.SMC[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        END_WB = END_WB + c.SMC[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
       });
       ERRWAT = END_WB - BEG_WB - (f.PRCP - w.ECAN - w.ETRAN - EDIR - w.runsrf - w.runsub) * DT;
     }
@@ -268,8 +266,8 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
 
     {  // added instrumentation: non-finite prognostics
       bool bad = !isfinite(c.TV) || !isfinite(c.TG) || !isfinite(c.sneqv) || !isfinite(c.ZWT) || !isfinite(c.WA);
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- bad = bad || !isfinite(c.STC[IX7(k)]) || !isfinite(c.SMC[IX4(k)]);
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        bad = bad || !isfinite(c.STC[IX7(k)]) || !isfinite(c.SMC[IX4(k)]);
       });
       if (bad) flags |= FLAG_NAN;
     }
@@ -300,9 +298,9 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     S[S_CANLIQ * n] = c.CANLIQ; S[S_CANICE * n] = c.CANICE; S[S_TV * n] = c.TV; S[S_TG * n] = c.TG;
     S[S_QSNOW * n] = c.QSNOW; S[S_ISNOW * n] = __int_as_float(c.ISNOW); S[S_SNOWH * n] = c.snowh;
     S[S_SNEQV * n] = c.sneqv; S[S_ZWT * n] = c.ZWT; S[S_WA * n] = c.WA; S[S_WT * n] = c.WT; S[S_TAUSS * n] = c.TAUSS;
-static_for<0, (7) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_STC + k) * n] = c.STC[k]; S[(S_ZSNSO + k) * n] = c.ZSNSO[k]; });
-static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_SOILWAT + k) * n] = c.soilwat[k]; S[(S_SMC + k) * n] = c.SMC[k]; });
-static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_SNICE + k) * n] = c.SNICE[k]; S[(S_SNLIQ + k) * n] = c.SNLIQ[k]; });
+    static_for<0, (7) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_STC + k) * n] = c.STC[k]; S[(S_ZSNSO + k) * n] = c.ZSNSO[k]; });
+    static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_SOILWAT + k) * n] = c.soilwat[k]; S[(S_SMC + k) * n] = c.SMC[k]; });
+    static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(S_SNICE + k) * n] = c.SNICE[k]; S[(S_SNLIQ + k) * n] = c.SNLIQ[k]; });
     if (EXT) {
       S[S_QSFC * n] = c.QSFC; S[S_TAH * n] = c.TAH; S[S_CM * n] = c.CM; S[S_CH * n] = c.CH; S[S_WSLAKE * n] = c.WSLAKE;
       S[S_LFMASS * n] = c.LFMASS; S[S_RTMASS * n] = c.RTMASS; S[S_STMASS * n] = c.STMASS; S[S_WOOD * n] = c.WOOD;
@@ -315,7 +313,7 @@ static_for<0, (3) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value; S[(
     const double on = (active && !badtype) ? 1.0 : 0.0;
     const double fin = (active && a.final_launch) ? 1.0 : 0.0;
     double soilw = 0.0;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       const float thick = (k == 1) ? -rc.zsoil[0] : (rc.zsoil[k > 1 ? k - 2 : 0] - rc.zsoil[k - 1]);
       soilw += (double)(c.SMC[IX4(k)] * thick * 1000.0f);
     });
@@ -325,7 +323,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     v[B_FIRA] = on * b_fira; v[B_FSH] = on * b_fsh; v[B_LH] = on * b_lh; v[B_SSOIL] = on * b_ssoil;
     v[B_PRCP_DT] = on * b_prcp; v[B_ET_DT] = on * b_et; v[B_RUNOFF_DT] = on * b_runoff;
     v[B_SNEQV] = fin * on * (double)c.sneqv; v[B_SOILWATER] = fin * on * soilw;
-static_for<0, (NBUDGET) - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
+    static_for<0, (NBUDGET) - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
       const double r = (q == B_ERRWAT_MAXABS) ? warp_max(v[q]) : warp_sum(v[q]);
       if ((threadIdx.x & 31) == 0) {
         if (q == B_ERRWAT_MAXABS) {

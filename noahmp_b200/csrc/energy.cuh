@@ -708,7 +708,7 @@ __device__ __noinline__ void loop1_job(const Opt& opt, float (*xch)[LOOP1_CAP], 
 
 // ---- func:322-328  layer thickness from the interface depths ------------------------------------------
 __device__ __forceinline__ void layer_thickness(const Column& c, float (&DZSNSO)[7]) {
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+  static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (k == c.ISNOW + 1) DZSNSO[IX7(k)] = -c.ZSNSO[IX7(k)];
     else if (k > c.ISNOW + 1) DZSNSO[IX7(k)] = c.ZSNSO[IX7(k > -2 ? k - 1 : k)] - c.ZSNSO[IX7(k)];
     else DZSNSO[IX7(k)] = 0.0f;
@@ -718,7 +718,7 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
 // the depths opaque, so the optimiser cannot merge this with the first evaluation and keep seven registers (or
 // spill slots) alive across the Newton loops.  No instruction is generated for it.
 __device__ __forceinline__ void layer_thickness_again(Column& c, float (&DZSNSO)[7]) {
-static_for<0, 6>([&](auto k_) { constexpr int k = decltype(k_)::value; asm volatile("" : "+f"(c.ZSNSO[k])); });
+  static_for<0, 6>([&](auto k_) { constexpr int k = decltype(k_)::value; asm volatile("" : "+f"(c.ZSNSO[k])); });
   layer_thickness(c, DZSNSO);
 }
 
@@ -738,7 +738,7 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
   const float DT = rc.dt;
   const int ISNOW = c.ISNOW;
   float DZSNSO[7];   // re-derived before tsnosoi (layer_thickness_again), not kept across the flux solvers
-static_for<0, 6>([&](auto k_) { constexpr int k = decltype(k_)::value; DZSNSO[k] = DZSNSO_in[k]; });
+  static_for<0, 6>([&](auto k_) { constexpr int k = decltype(k_)::value; DZSNSO[k] = DZSNSO_in[k]; });
   const float SMCMAX = SP[P_SMCMAX], BEXP = SP[P_BEXP], PSISAT = SP[P_PSISAT], SMCWLT = SP[P_SMCWLT];
   const float Z0 = 0.01f, PSIWLT = -150.0f;                                               // func:1017-1018
   r.flags = 0;
@@ -779,7 +779,7 @@ static_for<0, 6>([&](auto k_) { constexpr int k = decltype(k_)::value; DZSNSO[k]
   float DF1, DFtop;
   {
     float DFS[3];
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
       DFS[IX3(k)] = 0.0f;
       if (k >= ISNOW + 1) {
         const float BDSNOI = (c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)]) / DZSNSO[IX7(k)];        // func:1482-1490
@@ -808,7 +808,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
   ts.GDIR = 0.0f;
   if (day) {
     const float WL = elai / fmax2(VAI, MPE), WS = esai / fmax2(VAI, MPE);                 // func:1827-1833
-static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
+    static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
       RHO[ib] = fmax2(VG[V_RHOL + ib] * WL + VG[V_RHOS + ib] * WS, MPE);
       TAU[ib] = fmax2(VG[V_TAUL + ib] * WL + VG[V_TAUS + ib] * WS, MPE);
     });
@@ -842,7 +842,7 @@ static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
     }
     // groundalb, func:2154-2212
     const float INC = fmax2(0.11f - 0.40f * c.SMC[0], 0.0f);
-static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
+    static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
       float ALBSOD, ALBSOI;
       if (c.IST == 1) {
         ALBSOD = fmin2(T.color[(c.ISC - 1) * NCOLORP + K_ALBSAT + ib] + INC, T.color[(c.ISC - 1) * NCOLORP + K_ALBDRY + ib]);
@@ -872,7 +872,7 @@ static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
       twostream_band(ts, ic, VAI, c.FWET, c.TV, ib ? ALBGRD[1] : ALBGRD[0], ib ? ALBGRI[1] : ALBGRI[0],
                      ib ? RHO[1] : RHO[0], ib ? TAU[1] : TAU[0], T.gen[G_OMEGAS + ib], T.gen[G_BETADS],
                      T.gen[G_BETAIS], o);
-static_for<0, (2) - 1>([&](auto b_) { constexpr int b = decltype(b_)::value;
+      static_for<0, (2) - 1>([&](auto b_) { constexpr int b = decltype(b_)::value;
         if (ib == b && ic == 0) { FABD[b] = o.FAB; ALBD[b] = o.FRE; FTDD[b] = o.FTD; FTID[b] = o.FTI; FREVD[b] = o.FREV; FREGD[b] = o.FREG; }
         if (ib == b && ic == 1) { FABI[b] = o.FAB; ALBI[b] = o.FRE; FTII[b] = o.FTI; FREVI[b] = o.FREV; FREGI[b] = o.FREG; }
       });
@@ -892,7 +892,7 @@ static_for<0, (2) - 1>([&](auto b_) { constexpr int b = decltype(b_)::value;
   const float SOLAI[2] = {SWDOWN * 0.3f * 0.5f, SWDOWN * 0.3f * 0.5f};
   {
     float CAD[2], CAI[2];
-static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
+    static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
       CAD[ib] = SOLAD[ib] * FABD[ib];
       CAI[ib] = SOLAI[ib] * FABI[ib];
       SAV = SAV + CAD[ib] + CAI[ib];
@@ -932,12 +932,12 @@ static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
 
   const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
   float BTRAN = 0.0f;
-static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
- r.BTRANI[k] = 0.0f;
+  static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    r.BTRANI[k] = 0.0f;
   });
   if (c.IST == 1) {                                                                       // func:1119-1140
     const float zroot = -pick(rc.zsoil, NROOT - 1);
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       if (k <= NROOT) {
         float GX = 0.0f;
         if (opt.btr == 1) GX = (c.soilwat[IX4(k)] - SMCWLT) / (SP[P_SMCREF] - (SMCWLT));
@@ -952,8 +952,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       }
     });
     BTRAN = fmax2(MPE, BTRAN);
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+    static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       if (k <= NROOT) r.BTRANI[IX4(k)] = r.BTRANI[IX4(k)] / BTRAN;
     });
   }
@@ -1343,7 +1342,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   // 1420-1430) and FACT (1434-1436)
   layer_thickness_again(c, DZSNSO);
   float DF[7], HCPCT[7], FACT[7];
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
+  static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     HCPCT[IX7(k)] = 0.0f; DF[IX7(k)] = 0.0f;
     if (k >= ISNOW + 1) {
       const float dz = DZSNSO[IX7(k)];
@@ -1356,7 +1355,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     }
   });
   DF[IX7(1)] = DF1;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+  static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (k >= 2) {
       NMP_PHASE_SYNC_AT(4);
       DF[IX7(k)] = tdfcnd(SMCMAX, SP[P_QUARTZ], c.SMC[IX4(k)], c.soilwat[IX4(k)]);
@@ -1370,7 +1369,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       else { HCPCT[IX7(k)] = CICE; if (k >= 2) DF[IX7(k)] = TKICE; }
     }
   });
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+  static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     FACT[IX7(k)] = (k >= ISNOW + 1) ? DT / (HCPCT[IX7(k)] * DZSNSO[IX7(k)]) : 0.0f;
   });
   // ---- tsnosoi: hrt + hstep + rosr12, func:3987-4288 ---------------------------------------------
@@ -1378,7 +1377,7 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     const float ZBOTSNO = T.gen[G_ZBOT] - c.snowh;                                        // func:4039
     float AI[7], BI[7], CI[7], RHS[7];
     float dtsdz_prev = 0.0f, ddz_prev = 0.0f;
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                   // func:4139-4186 (two passes fused)
+    static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                   // func:4139-4186 (two passes fused)
       AI[IX7(k)] = 0.0f; BI[IX7(k)] = 0.0f; CI[IX7(k)] = 0.0f; RHS[IX7(k)] = 0.0f;
       if (k >= ISNOW + 1) {
         float DENOM, DDZ = 0.0f, DTSDZ = 0.0f, EFLUX;
@@ -1420,7 +1419,7 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;     
     });
     // hstep (func:4213-4235) + rosr12 (func:4268-4287): Thomas algorithm on layers ISNOW+1..4
     float P[7], DELTA[7];
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       P[IX7(k)] = 0.0f; DELTA[IX7(k)] = 0.0f;
       if (k >= ISNOW + 1) {
         const float rhs = RHS[IX7(k)] * DT, a = AI[IX7(k)] * DT, b = 1.0f + BI[IX7(k)] * DT;
@@ -1436,11 +1435,10 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       }
     });
     P[IX7(NSOIL)] = DELTA[IX7(NSOIL)];
-static_for_rev<NSOIL - 1, -2>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    static_for_rev<NSOIL - 1, -2>([&](auto k_) { constexpr int k = decltype(k_)::value;
       if (k >= ISNOW + 1) P[IX7(k)] = P[IX7(k)] * P[IX7(k + 1)] + DELTA[IX7(k)];
     });
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+    static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       if (k >= ISNOW + 1) c.STC[IX7(k)] = c.STC[IX7(k)] + P[IX7(k)];
     });
   }
@@ -1457,7 +1455,7 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   // ---- phasechange, func:4291-4491 (layers are independent: one pass, per-layer scalars) ---------
   {
     float QMELT = 0.0f, PONDING = 0.0f;
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       if (k <= 0) r.IMELT_snow[IX3(k <= 0 ? k : 0)] = 0;
       if (k >= ISNOW + 1) {
         float MICE, MLIQ, SUPERCOOL = 0.0f;

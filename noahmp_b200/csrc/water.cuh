@@ -203,11 +203,11 @@ __device__ __noinline__ void divide(SnowPack& s) {
 }
 
 __device__ __forceinline__ void pack_snow(const Column& c, const float (&DZSNSO)[7], SnowPack& s) {
-static_for<0, (3) - 1>([&](auto i_) { constexpr int i = decltype(i_)::value; s.dz[i] = DZSNSO[i]; s.ice[i] = c.SNICE[i]; s.liq[i] = c.SNLIQ[i]; s.t[i] = c.STC[i]; });
+  static_for<0, (3) - 1>([&](auto i_) { constexpr int i = decltype(i_)::value; s.dz[i] = DZSNSO[i]; s.ice[i] = c.SNICE[i]; s.liq[i] = c.SNLIQ[i]; s.t[i] = c.STC[i]; });
   s.isnow = c.ISNOW; s.soilwat1 = c.soilwat[0]; s.snowh = c.snowh; s.sneqv = c.sneqv;
 }
 __device__ __forceinline__ void unpack_snow(const SnowPack& s, Column& c, float (&DZSNSO)[7]) {
-static_for<0, (3) - 1>([&](auto i_) { constexpr int i = decltype(i_)::value; DZSNSO[i] = s.dz[i]; c.SNICE[i] = s.ice[i]; c.SNLIQ[i] = s.liq[i]; c.STC[i] = s.t[i]; });
+  static_for<0, (3) - 1>([&](auto i_) { constexpr int i = decltype(i_)::value; DZSNSO[i] = s.dz[i]; c.SNICE[i] = s.ice[i]; c.SNLIQ[i] = s.liq[i]; c.STC[i] = s.t[i]; });
   c.ISNOW = s.isnow; c.soilwat[0] = s.soilwat1; c.snowh = s.snowh; c.sneqv = s.sneqv;
 }
 
@@ -369,8 +369,7 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
       c.SNLIQ[IX3(0)] = 0.0f;
     }
     if (c.ISNOW < 0 && NEWNODE == 0 && QSNOW > 0.0f) {
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+      static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k == c.ISNOW + 1) {
           c.SNICE[IX3(k)] = c.SNICE[IX3(k)] + QSNOW * DT;
           DZSNSO[IX7(k)] = DZSNSO[IX7(k)] + snowhin * DT;
@@ -380,7 +379,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (c.ISNOW < 0) {
       // compact, func:5580-5677
       float BURDEN = 0.0f;
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k >= c.ISNOW + 1) {
           const float WX = c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)];
           const float FICE = c.SNICE[IX3(k)] / WX;
@@ -436,8 +435,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (c.snowh <= 1.0E-8f || c.sneqv <= 1.0E-6f) { c.snowh = 0.0f; c.sneqv = 0.0f; }     // func:5756-5759
     if (c.ISNOW < 0) {                                                                    // func:5763-5778
       float WGDIF = 0.0f;
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+      static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k == c.ISNOW + 1) {
           WGDIF = c.SNICE[IX3(k)] - QSNSUB * DT + QSNFRO * DT;
           c.SNICE[IX3(k)] = WGDIF;
@@ -452,8 +450,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         PONDING1 = s.ponding1; PONDING2 = s.ponding2; soilice[0] = s.soilice1;
       }
       if (c.ISNOW < 0) {
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+        static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
           if (k == c.ISNOW + 1) {
             c.SNLIQ[IX3(k)] = c.SNLIQ[IX3(k)] + QRAIN * DT;
             c.SNLIQ[IX3(k)] = fmax2(0.0f, c.SNLIQ[IX3(k)]);
@@ -463,8 +460,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     }
     {                                                                                     // func:5784-5818 percolation
       float VOL_LIQ[3] = {0.0f, 0.0f, 0.0f}, VOL_ICE[3] = {0.0f, 0.0f, 0.0f}, epore[3] = {0.0f, 0.0f, 0.0f};
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+      static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k >= c.ISNOW + 1) {
           VOL_ICE[IX3(k)] = fmin2(1.0f, c.SNICE[IX3(k)] / (DZSNSO[IX7(k)] * DENICE));
           epore[IX3(k)] = 1.0f - VOL_ICE[IX3(k)];
@@ -472,8 +468,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         }
       });
       float QIN = 0.0f, QOUT = 0.0f;
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+      static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k >= c.ISNOW + 1) {
           c.SNLIQ[IX3(k)] = c.SNLIQ[IX3(k)] + QIN;
           if (k <= -1) {
@@ -495,8 +490,7 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
       QSNBOT = QOUT / DT;
     }
     // back in snowwater: func:5127-5172
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+    static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
       if (k <= c.ISNOW) {
         c.SNICE[IX3(k)] = 0.0f; c.SNLIQ[IX3(k)] = 0.0f; c.STC[IX7(k)] = 0.0f; DZSNSO[IX7(k)] = 0.0f; c.ZSNSO[IX7(k)] = 0.0f;
       }
@@ -510,24 +504,23 @@ static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
     }
     if (c.ISNOW < 0) {                                                                    // func:5147-5152
       c.sneqv = 0.0f;
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+      static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k >= c.ISNOW + 1) c.sneqv = c.sneqv + c.SNICE[IX3(k)] + c.SNLIQ[IX3(k)];
       });
     }
-static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
+                                                       static_for<-2, 0>([&](auto k_) { constexpr int k = decltype(k_)::value;
                                                          // func:5156-5158
       if (k >= c.ISNOW + 1) DZSNSO[IX7(k)] = -DZSNSO[IX7(k)];
     });
     DZSNSO[IX7(1)] = rc.zsoil[0];                                                         // func:5160-5163
-static_for<2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- DZSNSO[IX7(k)] = (rc.zsoil[k - 1] - rc.zsoil[k - 2]);
+    static_for<2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      DZSNSO[IX7(k)] = (rc.zsoil[k - 1] - rc.zsoil[k - 2]);
     });
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                   // func:5165-5168
+    static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                   // func:5165-5168
       if (k == c.ISNOW + 1) c.ZSNSO[IX7(k)] = DZSNSO[IX7(k)];
       else if (k > c.ISNOW + 1) c.ZSNSO[IX7(k)] = c.ZSNSO[IX7(k > -2 ? k - 1 : k)] + DZSNSO[IX7(k)];
     });
-static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+                                                   static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
                                                      // func:5170-5172
       if (k >= c.ISNOW + 1) DZSNSO[IX7(k)] = -DZSNSO[IX7(k)];
     });
@@ -547,8 +540,8 @@ static_for<-2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   QSEVA = QSEVA * 0.001f;                                                                 // func:4766
   const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
   float ETRANI[4];
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- ETRANI[IX4(k)] = (k <= NROOT) ? w.ETRAN * e.BTRANI[IX4(k)] * 0.001f : 0.0f;
+  static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+    ETRANI[IX4(k)] = (k <= NROOT) ? w.ETRAN * e.BTRANI[IX4(k)] * 0.001f : 0.0f;
   });  // func:4768-4770
 
   if (c.IST == 2) {                                                                       // func:4774-4777 lake bucket
@@ -565,26 +558,26 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
   float dtfine = DT, QDRAIN_SAVE = 0.0f;
   NMP_PHASE_SYNC_AT(17);
   if (soil_col) {
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                    // func:5893-5897
+    static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                    // func:5893-5897
       const float epore = fmax2(1.0E-4f, (SMCMAX - soilice[IX4(k)]));
       RSAT = RSAT + fmax2(0.0f, c.soilwat[IX4(k)] - epore) * DZSNSO[IX7(k)];
       c.soilwat[IX4(k)] = fmin2(epore, c.soilwat[IX4(k)]);
     });
     {
       const float em4 = m_expf(-4.0f);
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                  // func:5900-5904
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                  // func:5900-5904
         const float FICE = fmin2(1.0f, soilice[IX4(k)] / SMCMAX);
         FCR[IX4(k)] = fmax2(0.0f, m_expf(-4.0f * (1.0f - FICE)) - em4) / (1.0f - em4);
       });
     }
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                    // func:5907-5914
+    static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                    // func:5907-5914
       if (soilice[IX4(k)] > SICEMAX) SICEMAX = soilice[IX4(k)];
       if (FCR[IX4(k)] > FCRMAX) FCRMAX = FCR[IX4(k)];
     });
     if (opt.run == 2) {                                                                   // func:5917-5922 + zwteq 6051-6100
       float WD1 = 0.0f;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- WD1 = WD1 + (SMCMAX - c.soilwat[IX4(k)]) * DZSNSO[IX7(k)];
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        WD1 = WD1 + (SMCMAX - c.soilwat[IX4(k)]) * DZSNSO[IX7(k)];
       });
       const float DZFINE = 3.0f * (-rc.zsoil[3]) / 100.0f;
       float ZWT = -3.0f * rc.zsoil[3] - 0.001f;
@@ -613,7 +606,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         const float DT1 = DT / 86400.0f;
         const float SMCAV = SMCMAX - SP[P_SMCWLT];
         float DD = 0.0f, DICE = 0.0f;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
           const float thick = (k == 1) ? -rc.zsoil[0] : (rc.zsoil[k > 1 ? k - 2 : 0] - rc.zsoil[k - 1]);
           float DMAX = thick * SMCAV;
           const float dice_k = thick * soilice[IX4(k)];
@@ -645,7 +638,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (opt.run == 4) {                                                                   // func:5953-5968
       float SMCTOT = 0.0f, DZTOT = 0.0f;
       bool done = false;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (!done) {
           DZTOT = DZTOT + DZSNSO[IX7(k)];
           SMCTOT = SMCTOT + c.SMC[IX4(k)] * DZSNSO[IX7(k)];
@@ -670,7 +663,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (soil_col && iter <= niter) {
       // srt, func:6199-6305
       float WDF[4], SMX[4], AI[4], BI[4], CI[4], RHS[4];
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (opt.inf == 1) {
           wdfcnd1(SMCMAX, BEXP, SP[P_DWSAT], SP[P_DKSAT], c.SMC[IX4(k)], FCR[IX4(k)], WDF[IX4(k)], WCND[IX4(k)]);
           SMX[IX4(k)] = c.SMC[IX4(k)];
@@ -680,7 +673,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         }
       });
       float dsmdz_prev = 0.0f, ddz_prev = 0.0f;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         float DENOM, DDZ = 0.0f, DSMDZ = 0.0f, WFLUX;
         if (k == 1) {
           DENOM = -rc.zsoil[0];
@@ -717,7 +710,7 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       });
       // sstep (func:6308-6383) + rosr12 (func:4240-4288) on 4 unknowns
       float P[4], DELTA[4];
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         const float rhs = RHS[IX4(k)] * dtfine, a = AI[IX4(k)] * dtfine, b = 1.0f + BI[IX4(k)] * dtfine;
         const float cc = (k == NSOIL) ? 0.0f : CI[IX4(k)] * dtfine;
         if (k == 1) {
@@ -729,14 +722,14 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         }
       });
       P[3] = DELTA[3];
-static_for_rev<NSOIL - 1, 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
- P[IX4(k)] = P[IX4(k)] * P[IX4(k + 1)] + DELTA[IX4(k)];
+      static_for_rev<NSOIL - 1, 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        P[IX4(k)] = P[IX4(k)] * P[IX4(k + 1)] + DELTA[IX4(k)];
       });
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- c.soilwat[IX4(k)] = c.soilwat[IX4(k)] + P[IX4(k)];
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        c.soilwat[IX4(k)] = c.soilwat[IX4(k)] + P[IX4(k)];
       });
       float WPLUS = 0.0f;
-static_for_rev<NSOIL, 2>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                  // func:6372-6377
+      static_for_rev<NSOIL, 2>([&](auto k_) { constexpr int k = decltype(k_)::value;                                                  // func:6372-6377
         const float epore = fmax2(1.0E-4f, SMCMAX - soilice[IX4(k)]);
         WPLUS = fmax2(c.soilwat[IX4(k)] - epore, 0.0f) * DZSNSO[IX7(k)];
         c.soilwat[IX4(k)] = fmin2(epore, c.soilwat[IX4(k)]);
@@ -747,8 +740,8 @@ static_for_rev<NSOIL, 2>([&](auto k_) { constexpr int k = decltype(k_)::value;  
         WPLUS = fmax2(c.soilwat[0] - epore, 0.0f) * DZSNSO[IX7(1)];
         c.soilwat[0] = fmin2(epore, c.soilwat[0]);
       }
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- c.SMC[IX4(k)] = c.soilwat[IX4(k)] + soilice[IX4(k)];
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        c.SMC[IX4(k)] = c.soilwat[IX4(k)] + soilice[IX4(k)];
       });
       RSAT = RSAT + WPLUS;
       QDRAIN_SAVE = QDRAIN_SAVE + QDRAIN;
@@ -761,21 +754,21 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     QDRAIN = QDRAIN * 1000.0f;
     if (opt.run == 2) {                                                                   // func:6004-6014
       float WTSUB = 0.0f;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- WTSUB = WTSUB + WCND[IX4(k)] * DZSNSO[IX7(k)];
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        WTSUB = WTSUB + WCND[IX4(k)] * DZSNSO[IX7(k)];
       });
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         const float MH2O = runsub * DT * (WCND[IX4(k)] * DZSNSO[IX7(k)]) / WTSUB;
         c.soilwat[IX4(k)] = c.soilwat[IX4(k)] - MH2O / (DZSNSO[IX7(k)] * 1000.0f);
       });
     }
     if (opt.run != 1) {                                                                   // func:6018-6046
       float MLIQ[4];
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- MLIQ[IX4(k)] = c.soilwat[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        MLIQ[IX4(k)] = c.soilwat[IX4(k)] * DZSNSO[IX7(k)] * 1000.0f;
       });
       const float WATMIN = 0.01f;
-static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
         const float XS = (MLIQ[IX4(k)] < 0.0f) ? WATMIN - MLIQ[IX4(k)] : 0.0f;
         MLIQ[IX4(k)] = MLIQ[IX4(k)] + XS;
         MLIQ[IX4(k + 1)] = MLIQ[IX4(k + 1)] - XS;
@@ -783,8 +776,8 @@ static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
       const float XS = (MLIQ[3] < WATMIN) ? WATMIN - MLIQ[3] : 0.0f;
       MLIQ[3] = MLIQ[3] + XS;
       runsub = runsub - XS / DT;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- c.soilwat[IX4(k)] = div_rn(MLIQ[IX4(k)], DZSNSO[IX7(k)] * 1000.0f);
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        c.soilwat[IX4(k)] = div_rn(MLIQ[IX4(k)], DZSNSO[IX7(k)] * 1000.0f);
       });
     }
     w.runsrf = runsrf;
@@ -795,19 +788,18 @@ static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       float DZMM[4], ZNODE[4], MLIQ[4], epore[4], HK[4], SMCg[4];
       DZMM[0] = -rc.zsoil[0] * 1.0E3f;
       ZNODE[0] = -rc.zsoil[0] / 2.0f;
-static_for<2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<2, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         DZMM[IX4(k)] = 1.0E3f * (rc.zsoil[k - 2] - rc.zsoil[k - 1]);
         ZNODE[IX4(k)] = -rc.zsoil[k - 2] + 0.5f * (rc.zsoil[k - 2] - rc.zsoil[k - 1]);
       });
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         SMCg[IX4(k)] = c.soilwat[IX4(k)] + soilice[IX4(k)];
         MLIQ[IX4(k)] = c.soilwat[IX4(k)] * DZMM[IX4(k)];
         epore[IX4(k)] = fmax2(0.01f, SMCMAX - soilice[IX4(k)]);
         HK[IX4(k)] = 1.0E3f * WCND[IX4(k)];
       });
       int IWT = NSOIL;                                                                    // func:6545-6551
-static_for_rev<NSOIL, 2>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+      static_for_rev<NSOIL, 2>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (c.ZWT <= -rc.zsoil[k - 1]) IWT = k - 1;
       });
       const float QDIS = (1.0f - FCRMAX) * 5.0f * m_expf(-T.gen[G_TIMEAN]) * m_expf(-6.0f * (c.ZWT - 2.0f));  // func:6557
@@ -840,23 +832,22 @@ static_for_rev<NSOIL, 2>([&](auto k_) { constexpr int k = decltype(k_)::value;
           c.ZWT = -rc.zsoil[3] - (c.WT - 0.2f * 1000.0f * 25.0f) / (epore[3]) / 1000.0f;
         } else {
           float WS = 0.0f;
-static_for<3, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+          static_for<3, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
             if (k >= IWT + 2) WS = WS + epore[IX4(k)] * DZMM[IX4(k)];
           });
           c.ZWT = -pick(rc.zsoil, IWT) - (c.WT - 0.2f * 1000.0f * 25.0f - WS) / (pick(epore, IWT)) / 1000.0f;
         }
         float WTSUB = 0.0f;                                                               // func:6599-6606
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- WTSUB = WTSUB + HK[IX4(k)] * DZMM[IX4(k)];
+        static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+          WTSUB = WTSUB + HK[IX4(k)] * DZMM[IX4(k)];
         });
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- MLIQ[IX4(k)] = MLIQ[IX4(k)] - QDIS * DT * HK[IX4(k)] * DZMM[IX4(k)] / WTSUB;
+        static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+          MLIQ[IX4(k)] = MLIQ[IX4(k)] - QDIS * DT * HK[IX4(k)] * DZMM[IX4(k)] / WTSUB;
         });
       }
       c.ZWT = fmax2(1.5f, c.ZWT);                                                         // func:6609
       const float WATMIN = 0.01f;                                                         // func:6615-6638
-static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
         const float XS = (MLIQ[IX4(k)] < 0.0f) ? WATMIN - MLIQ[IX4(k)] : 0.0f;
         MLIQ[IX4(k)] = MLIQ[IX4(k)] + XS;
         MLIQ[IX4(k + 1)] = MLIQ[IX4(k + 1)] - XS;
@@ -865,14 +856,14 @@ static_for<1, NSOIL - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
       MLIQ[3] = MLIQ[3] + XS;
       c.WA = c.WA - XS;
       c.WT = c.WT - XS;
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- c.soilwat[IX4(k)] = div_rn(MLIQ[IX4(k)], DZMM[IX4(k)]);
+      static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+        c.soilwat[IX4(k)] = div_rn(MLIQ[IX4(k)], DZMM[IX4(k)]);
       });
       w.runsub = QDIS;                                                                    // func:4790
     }
     if (opt.run == 3 || opt.run == 4) w.runsub = w.runsub + QDRAIN;                       // func:4793-4795
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
- c.SMC[IX4(k)] = c.soilwat[IX4(k)] + soilice[IX4(k)];
+    static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
+      c.SMC[IX4(k)] = c.soilwat[IX4(k)] + soilice[IX4(k)];
     }); // func:4797-4799
   }
   w.runsub = w.runsub + SNOFLOW;                                                          // func:4802
@@ -896,8 +887,7 @@ __device__ __forceinline__ void carbon(const Tables& T, const RunConst& rc, Colu
   const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
   float WROOT = 0.0f;
   const float zroot = -pick(rc.zsoil, NROOT - 1);
-static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
-
+  static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (k <= NROOT) WROOT = WROOT + c.SMC[IX4(k)] / SMCMAX * DZSNSO[IX7(k)] / zroot;
   });
   // co2flux, func:6754-7025
