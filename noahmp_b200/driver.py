@@ -83,11 +83,32 @@ def snow_layers_from_depth(snowh, sneqv, tsnow, zsoil=synth.ZSOIL):
     return isnow, dz, snice, zs
 
 
-def columns_from_init(path: str, tables: ParamTables) -> Columns:
+def initial_vegetation(tables: ParamTables, lutyp, lat_rad, when: dt.datetime | None):
+    """Initial LAI, SAI and carbon pools, following common upstream Noah-MP practice (WRF's NOAHMP_INIT; the reference has
+    no initialisation code): LAI / SAI from the monthly tables at the start date (southern hemisphere shifted by six
+    months, as phenology does, func:580-597), at least 0.05 / max(0.1 LAI, 0.05); leaf mass LAI x 1000 / max(SLA, 1),
+    stem mass SAI x 1000 / 3, root mass and wood 500, stable and fast soil carbon 1000 g/m2; all zero on urban, water,
+    barren and ice.  Only the dynamic-vegetation options (opt_veg 2 / 5, func:6642-7025) read the pools."""
+    lutyp = np.asarray(lutyp, np.int64)
+    month = (when.month if when is not None else 7) - 1
+    m = np.where(np.asarray(lat_rad) >= 0.0, month, (month + 6) % 12)
+    lai12 = np.stack([np.asarray(tables.veg_f[f"LAI{k:02d}"], f32) for k in range(1, 13)])     # [12][nvegtyp]
+    sai12 = np.stack([np.asarray(tables.veg_f[f"SAI{k:02d}"], f32) for k in range(1, 13)])
+    lai = np.maximum(lai12[m, lutyp - 1], f32(0.05))
+    sai = np.maximum(np.maximum(sai12[m, lutyp - 1], f32(0.1) * lai), f32(0.05))
+    sla = np.maximum(np.asarray(tables.veg_f["SLA"], f32)[lutyp - 1], f32(1.0))
+    pools = {"LAI": lai, "SAI": sai, "LFMASS": lai * (f32(1000.0) / sla), "STMASS": sai * f32(1000.0 / 3.0),
+             "RTMASS": np.full(lai.shape, 500.0, f32), "WOOD": np.full(lai.shape, 500.0, f32),
+             "STBLCP": np.full(lai.shape, 1000.0, f32), "FASTCP": np.full(lai.shape, 1000.0, f32)}
+    bare = np.isin(lutyp, [tables.flags[k] for k in ("ISURBAN", "ISWATER", "ISBARREN", "ISICE")])
+    return {k: np.where(bare, f32(0.0), v).astype(f32) for k, v in pools.items()}
+
+
+def columns_from_init(path: str, tables: ParamTables, when: dt.datetime | None = None, static_path: str | None = None) -> Columns:
     """``.npz`` keys: lat, lon [deg]; lutyp, sltyp, slptyp, isc (ints); shdfac, tbot; tsk (skin T), stc[4], smc[4],
     optional sh2o[4], snowh [m], sneqv [mm], canliq, zwt, wa.  A NetCDF-3 file with the HRLDAS / WRF variable names
     (``ncio.INIT_ALIASES``) is accepted as well; its grid is flattened row-major."""
-    z = ncio.read_init(path) if ncio.is_netcdf(path) else np.load(path)
+    z = ncio.read_init(path, static_path) if ncio.is_netcdf(path) else np.load(path)
     n = z["lat"].size
     st = synth._blank_state(n)
     sl = z["sltyp"].astype(np.int64)
@@ -124,9 +145,9 @@ def columns_from_init(path: str, tables: ParamTables) -> Columns:
     st[S["CM"]] = 0.1
     st[S["CH"]] = 0.1
     st[S["QSFC"]] = 0.005
-    st[S["LAI"]] = 2.0
-    st[S["SAI"]] = 0.5
     lat, lon = np.deg2rad(z["lat"].astype(np.float64)), np.deg2rad(z["lon"].astype(np.float64))
+    for name, val in initial_vegetation(tables, z["lutyp"], lat, when).items():
+        st[S[name]] = val
     sf = np.zeros((L.NSTATIC_F, n), f32)
     sf[L.C["LAT"]] = lat
     sf[L.C["SHDFAC"]] = get("shdfac", 0.7)
@@ -162,7 +183,7 @@ def run_files(cfg, device: int = 0, variant="fast", max_steps_per_launch: int = 
     import torch
     tables = (ParamTables.from_tbl_dir(cfg.table_directory, cfg.soil_table_tag, cfg.veg_table_tag)
               if getattr(cfg, "table_directory", None) else ParamTables.default(cfg.soil_table_tag, cfg.veg_table_tag))
-    cols = columns_from_init(cfg.initfile, tables)
+    cols = columns_from_init(cfg.initfile, tables, cfg.begdatetime, getattr(cfg, "constfile", None))
     as_nc = ncio.is_netcdf(cfg.initfile)    # outputs and restarts follow the format of the initialisation file
     t, step0 = cfg.begdatetime, 0
     res_path = cfg.resfile if os.path.isabs(str(cfg.resfile)) else os.path.join(cfg.resdir, str(cfg.resfile))

@@ -88,11 +88,15 @@ class InitData(dict):
         return list(self.keys())
 
 
-def read_init(path: str) -> InitData:
-    out = InitData()
+STATIC_KEYS = ("lat", "lon", "lutyp", "sltyp", "slptyp", "isc", "shdmax", "tbot")   # what a geo_em-style file may supply
+
+
+def _read_into(out: "InitData", path: str, keys) -> None:
     with _open(path) as nc:
-        for key, names in INIT_ALIASES.items():
-            name = next((n for n in names if n in nc.variables), None)
+        for key in keys:
+            if key in out:
+                continue
+            name = next((n for n in INIT_ALIASES[key] if n in nc.variables), None)
             if name is None:
                 continue
             a, dims = _squeeze_time(nc.variables[name])
@@ -102,6 +106,19 @@ def read_init(path: str) -> InitData:
             out[key] = a
             if key == "lat":
                 out.grid = tuple(grid)
+
+
+def read_init(path: str, static_path: str | None = None) -> InitData:
+    """The initialisation file; fields it lacks among ``STATIC_KEYS`` are taken from the namelist's
+    ``static_parameter_file`` (``geo_em.d01.nc``-style: XLAT XLONG LU_INDEX ...) when that is a NetCDF-3 file on the same grid."""
+    out = InitData()
+    _read_into(out, path, INIT_ALIASES)
+    if static_path and os.path.isfile(static_path) and is_netcdf(static_path):
+        _read_into(out, static_path, STATIC_KEYS)
+        n = out["lat"].size if "lat" in out else None
+        for key in STATIC_KEYS:
+            if key in out and n is not None and out[key].size != n:
+                raise ValueError(f"ERR: {static_path}: {key} has {out[key].size} cells, {path} has {n}")
     for need in ("lat", "lon", "lutyp", "sltyp", "tsk", "stc", "smc"):
         if need not in out:
             raise ValueError(f"ERR: {path} has none of {INIT_ALIASES[need]} (needed for {need})")

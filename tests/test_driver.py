@@ -184,3 +184,54 @@ def test_netcdf4_files_are_refused_with_a_hint(tmp_path):
     p.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
     with pytest.raises(ValueError, match="nccopy -k classic"):
         ncio.is_netcdf(str(p))
+
+
+def test_static_parameter_file_supplies_what_the_init_file_lacks(tmp_path, tables):
+    """geo_em-style static file (XLAT XLONG LU_INDEX ISLTYP) + an init file with only the prognostic fields."""
+    from scipy.io import netcdf_file
+    from noahmp_b200.driver import columns_from_init
+    init = _init_dict(48)
+    _write_wrf_style_init(str(tmp_path / "full.nc"), init, (6, 8))
+    with netcdf_file(str(tmp_path / "geo_em.d01.nc"), "w", version=2) as nc:
+        nc.createDimension("Time", 1)
+        nc.createDimension("south_north", 6)
+        nc.createDimension("west_east", 8)
+        for name, key, typ in (("XLAT", "lat", "f4"), ("XLONG", "lon", "f4"), ("LU_INDEX", "lutyp", "i4"), ("ISLTYP", "sltyp", "i4"),
+                               ("SLOPETYP", "slptyp", "i4"), ("ISC", "isc", "i4"), ("TMN", "tbot", "f4")):
+            v = nc.createVariable(name, typ, ("Time", "south_north", "west_east"))
+            v[:] = np.asarray(init[key]).astype(typ).reshape(1, 6, 8)
+    with netcdf_file(str(tmp_path / "init.nc"), "w", version=2) as nc:
+        nc.createDimension("Time", 1)
+        nc.createDimension("soil_layers_stag", 4)
+        nc.createDimension("south_north", 6)
+        nc.createDimension("west_east", 8)
+        for name, key in (("TSK", "tsk"), ("SNOWH", "snowh"), ("SNOW", "sneqv")):
+            v = nc.createVariable(name, "f4", ("Time", "south_north", "west_east"))
+            v[:] = np.asarray(init[key], np.float32).reshape(1, 6, 8)
+        v = nc.createVariable("VEGFRA", "f4", ("Time", "south_north", "west_east"))
+        v[:] = (np.asarray(init["shdfac"], np.float32) * np.float32(100.0)).reshape(1, 6, 8)
+        for name, key in (("TSLB", "stc"), ("SMOIS", "smc")):
+            v = nc.createVariable(name, "f4", ("Time", "soil_layers_stag", "south_north", "west_east"))
+            v[:] = np.asarray(init[key], np.float32).reshape(1, 4, 6, 8)
+    with pytest.raises(ValueError, match="XLAT"):
+        columns_from_init(str(tmp_path / "init.nc"), tables)
+    a = columns_from_init(str(tmp_path / "full.nc"), tables)
+    b = columns_from_init(str(tmp_path / "init.nc"), tables, static_path=str(tmp_path / "geo_em.d01.nc"))
+    assert b.grid == (6, 8) and np.array_equal(a.state.view(np.int32), b.state.view(np.int32))
+    assert np.array_equal(a.static_f.view(np.int32), b.static_f.view(np.int32)) and np.array_equal(a.static_i, b.static_i)
+
+
+def test_initial_vegetation_pools(tables):
+    from noahmp_b200.driver import initial_vegetation
+    lut = np.array([tables.flags["ISURBAN"], tables.flags["ISWATER"], tables.flags["ISBARREN"], tables.flags["ISICE"], 7, 7, 11, 14])
+    lat = np.radians([40.0, 40.0, 40.0, 70.0, 40.0, -40.0, 45.0, 60.0])
+    v = initial_vegetation(tables, lut, lat, dt.datetime(2000, 7, 1))
+    for name in ("LAI", "SAI", "LFMASS", "STMASS", "RTMASS", "WOOD", "STBLCP", "FASTCP"):
+        assert (v[name][:4] == 0).all() and (v[name][4:] > 0).all(), name
+    lai7 = np.asarray(tables.veg_f["LAI07"], np.float32)
+    lai1 = np.asarray(tables.veg_f["LAI01"], np.float32)
+    assert v["LAI"][4] == max(lai7[6], np.float32(0.05)) and v["LAI"][5] == max(lai1[6], np.float32(0.05))   # hemisphere shift
+    sla = np.asarray(tables.veg_f["SLA"], np.float32)
+    assert np.isclose(v["LFMASS"][6], v["LAI"][6] * 1000.0 / max(sla[10], 1.0), rtol=1e-6)
+    assert np.isclose(v["STMASS"][7], v["SAI"][7] * 1000.0 / 3.0, rtol=1e-6) and v["WOOD"][7] == 500.0 and v["FASTCP"][7] == 1000.0
+    assert (v["SAI"][4:] >= np.maximum(np.float32(0.1) * v["LAI"][4:], np.float32(0.05)) - 1e-7).all()

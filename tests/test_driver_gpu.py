@@ -32,7 +32,7 @@ def test_prepare_forcing_bit_exact(tables, ncol):
     eng.close()
 
 
-def _make_case(tmp_path, ncol=96, hours=7):
+def _make_case(tmp_path, ncol=96, hours=7, opt_veg=1):
     """Write an init file, hourly forcing records and a namelist; return the Config."""
     import noahmp_config
     w = synth.make_workload("global025", ncol=ncol, nsteps=1)
@@ -57,7 +57,7 @@ def _make_case(tmp_path, ncol=96, hours=7):
       start_year = 2000, start_month = 6, start_day = 30, start_hour = 22, start_minute = 0, start_second = 0,
       end_year = 2000, end_month = 7, end_day = 1, end_hour = {22 + hours - 24}, end_minute = 0, end_second = 0,
       interval_seconds = 900,
-      opt_veg = 1, opt_run = 1, opt_btr = 1, opt_rad = 1, opt_tub = 1, opt_can = 1, opt_inf = 1, opt_tbot = 1, opt_snf = 1
+      opt_veg = {opt_veg}, opt_run = 1, opt_btr = 1, opt_rad = 1, opt_tub = 1, opt_can = 1, opt_inf = 1, opt_tbot = 1, opt_snf = 1
     /"""
     (tmp_path / "case.nml").write_text(nml)
     return noahmp_config.Config(str(tmp_path / "case.nml"))
@@ -125,6 +125,22 @@ def test_netcdf_driven_run_equals_the_npz_driven_run(tmp_path, tables):
     assert np.array_equal(st.view(np.int32), ref_state.view(np.int32))
     out, _, _ = ncio.read_planes(str(tmp_path / "b" / "out" / "200007010100.LDASOUT_DOMAIN1"), L.DIAG, int_planes=("ITER", "FLAGS"))
     assert np.isfinite(out[L.D["TRAD"]]).all()
+
+
+def test_dynamic_vegetation_run_starts_with_a_canopy(tmp_path, tables):
+    """opt_veg = 2 reads LAI/SAI and the carbon pools from the state: the driver initialises them from the tables."""
+    from noahmp_b200.driver import columns_from_init, read_restart, run_files
+    cfg = _make_case(tmp_path, hours=4, opt_veg=2)
+    out = run_files(cfg, variant="parity")
+    assert out["steps"] == 16 and out["flagged_column_launches"] == 0
+    st, _, _ = read_restart(str(tmp_path / "restart" / "RESTART.200007010200.npz"))
+    c0 = columns_from_init(cfg.initfile, tables, cfg.begdatetime)
+    veg = c0.state[L.S["LFMASS"]] > 0
+    assert veg.sum() > 10 and (~veg).sum() > 0                          # vegetated and barren/ice/water columns both present
+    assert (st[L.S["LAI"]][veg] >= 0.05).all() and (st[L.S["LAI"]][~veg] == 0).all()
+    assert (st[L.S["LFMASS"]][veg] != c0.state[L.S["LFMASS"]][veg]).mean() > 0.9     # the pools evolve (func:6642-7025)
+    dg = np.load(tmp_path / "out" / "200007010100.LDASOUT.npz")["diag"]
+    assert (dg[L.D["FVEG"]][veg] > 0.01).all() and np.isfinite(dg[L.D["NPP"]]).all()
 
 
 def test_main_entry_point_runs_the_synthetic_single_point(tmp_path):
