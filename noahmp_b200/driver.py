@@ -177,10 +177,25 @@ def read_restart(path: str):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_files(cfg, device: int = 0, variant="fast", max_steps_per_launch: int = 24) -> dict:
+def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_launch: int = 24) -> dict:
     """The file-driven time loop.  Forcing valid at the start of each step; launches are cut at output and restart
-    boundaries and otherwise fuse up to ``max_steps_per_launch`` steps."""
+    boundaries and otherwise fuse up to ``max_steps_per_launch`` steps.
+
+    Under ``torchrun`` (WORLD_SIZE > 1) every rank advances its block of columns (``parallel.shard``) on its own GPU with no
+    exchange on the step path; at output / restart boundaries the planes are all-gathered and rank 0 writes the files, and
+    the budget sums are all-reduced at the end."""
     import torch
+    import torch.distributed as dist
+    from .parallel import allreduce_budget, gather_columns, shard
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", device)
+    own_group = False
+    if world > 1 and not dist.is_initialized():
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=dev)
+        own_group = True
     tables = (ParamTables.from_tbl_dir(cfg.table_directory, cfg.soil_table_tag, cfg.veg_table_tag)
               if getattr(cfg, "table_directory", None) else ParamTables.default(cfg.soil_table_tag, cfg.veg_table_tag))
     cols = columns_from_init(cfg.initfile, tables, cfg.begdatetime, getattr(cfg, "constfile", None))
@@ -191,22 +206,25 @@ def run_files(cfg, device: int = 0, variant="fast", max_steps_per_launch: int = 
         cols.state, t, step0 = read_restart(res_path)
     dtm = cfg.timestep
     out_freq, res_freq = F.parse_frequency(cfg.outfreq), F.parse_frequency(cfg.resfreq)
-    dev = torch.device("cuda", device)
     eng = NoahMP(tables, cfg.physics_options(), device=device, fast=variant)
-    ncol = cols.ncol
-    state = torch.from_numpy(cols.state).to(dev)
-    sf, si = torch.from_numpy(cols.static_f).to(dev), torch.from_numpy(cols.static_i).to(dev)
-    geo = torch.from_numpy(F.geo_planes(cols.lat, cols.lon)).to(dev)
+    ntot = cols.ncol
+    c0, ncol = shard(ntot, rank, world)
+    mine = slice(c0, c0 + ncol)
+    state = torch.from_numpy(np.ascontiguousarray(cols.state[:, mine])).to(dev)
+    sf = torch.from_numpy(np.ascontiguousarray(cols.static_f[:, mine])).to(dev)
+    si = torch.from_numpy(np.ascontiguousarray(cols.static_i[mine])).to(dev)
+    geo = torch.from_numpy(np.ascontiguousarray(F.geo_planes(cols.lat, cols.lon)[:, mine])).to(dev)
     diag = torch.zeros((L.NDIAG, ncol), dtype=torch.float32, device=dev)
     budget = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
     forcing = torch.empty((max_steps_per_launch, L.NFORCING, ncol), dtype=torch.float32, device=dev)
-    reader = F.RecordReader(cfg.indir, cfg.infreq, cfg.begdatetime, ncol, dev)
+    reader = F.RecordReader(cfg.indir, cfg.infreq, cfg.begdatetime, ntot, dev)
+    rec = (lambda when: reader.record(when)[:, mine].contiguous()) if world > 1 else reader.record
     nsteps, written = step0, []
     while t < cfg.enddatetime:
         t_launch, g = t, 0
         while g < max_steps_per_launch and t < cfg.enddatetime:
             t0, t1, wgt = reader.bracket(t)
-            eng.prepare_forcing(reader.record(t0), reader.record(t1), wgt, geo, F.solar_scalars(t), forcing[g])
+            eng.prepare_forcing(rec(t0), rec(t1), wgt, geo, F.solar_scalars(t), forcing[g])
             g += 1
             t = t + dtm
             if F.is_boundary(t, cfg.begdatetime, out_freq) or F.is_boundary(t, cfg.begdatetime, res_freq):
@@ -215,28 +233,41 @@ def run_files(cfg, device: int = 0, variant="fast", max_steps_per_launch: int = 
         eng.run(rp, state, forcing[:g], sf, si, diag, budget)
         nsteps += g
         if F.is_boundary(t, cfg.begdatetime, out_freq):
-            os.makedirs(cfg.outdir, exist_ok=True)
+            full = gather_columns(diag, ntot).cpu().numpy()
             if as_nc:
                 p = os.path.join(cfg.outdir, F.stamp(t) + ".LDASOUT_DOMAIN1")
-                ncio.write_output(p, diag.cpu().numpy(), t, cols.grid)
             else:
                 p = os.path.join(cfg.outdir, F.stamp(t) + ".LDASOUT.npz")
-                np.savez(p, diag=diag.cpu().numpy(), planes=np.asarray(L.DIAG), time=F.stamp(t))
+            if rank == 0:
+                os.makedirs(cfg.outdir, exist_ok=True)
+                if as_nc:
+                    ncio.write_output(p, full, t, cols.grid)
+                else:
+                    np.savez(p, diag=full, planes=np.asarray(L.DIAG), time=F.stamp(t))
             written.append(p)
         if F.is_boundary(t, cfg.begdatetime, res_freq):
+            full = gather_columns(state, ntot).cpu().numpy()
             if as_nc:
                 p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + "_DOMAIN1")
-                ncio.write_restart(p, state.cpu().numpy(), t, nsteps, cols.grid)
             else:
                 p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + ".npz")
-                write_restart(p, state.cpu().numpy(), t, nsteps)
+            if rank == 0:
+                if as_nc:
+                    ncio.write_restart(p, full, t, nsteps, cols.grid)
+                else:
+                    write_restart(p, full, t, nsteps)
             written.append(p)
     torch.cuda.synchronize()
-    out = _summary(state.cpu().numpy(), diag.cpu().numpy(), budget.cpu().numpy(), ncol, nsteps, dtm.total_seconds(),
-                   cfg.physics_options())
+    allreduce_budget(budget)
+    out = _summary(gather_columns(state, ntot).cpu().numpy(), gather_columns(diag, ntot).cpu().numpy(), budget.cpu().numpy(), ntot,
+                   nsteps, dtm.total_seconds(), cfg.physics_options())
     out["files_written"] = written
     out["launches"] = eng.launch_count()
+    out["ranks"] = world
     eng.close()
+    if own_group:
+        dist.barrier()
+        dist.destroy_process_group()
     return out
 
 
@@ -260,7 +291,7 @@ def steps_of(cfg) -> int:
 def run_case(cfg, ncol: int = 1, chunk: int = 96, device: int = 0, variant="fast") -> dict:
     """Entry used by run/main.py: file driven when the namelist's initialization file exists, else synthetic."""
     if os.path.isfile(str(cfg.initfile)):
-        return run_files(cfg, device=device, variant=variant)
+        return run_files(cfg, device=device if "LOCAL_RANK" not in os.environ else None, variant=variant)
     import torch
     tables = (ParamTables.from_tbl_dir(cfg.table_directory, cfg.soil_table_tag, cfg.veg_table_tag)
               if getattr(cfg, "table_directory", None) else ParamTables.default(cfg.soil_table_tag, cfg.veg_table_tag))

@@ -54,6 +54,22 @@ def allreduce_budget(budget, group=None):
     return budget
 
 
+def gather_columns(local, ncol: int, group=None):
+    """[P][nloc] shards of the block partition of :func:`shard` -> the full [P][ncol] tensor on every rank (all-gather of
+    equal-size padded blocks; used at output / restart cadence only, never on the step path)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    per = (ncol + world - 1) // world
+    pad = torch.zeros((local.shape[0], per), dtype=local.dtype, device=local.device)
+    pad[:, :local.shape[1]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat(parts, dim=1)[:, :ncol].contiguous()
+
+
 def budget_means(budget, nsteps: int) -> dict:
     """Domain means per cell (and per step for fluxes) from the reduced sums."""
     b = {n: float(budget[i]) for i, n in enumerate(L.BUDGET)}

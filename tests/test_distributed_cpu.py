@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from conftest import ROOT
 from noahmp_b200 import layout as L, synth
-from noahmp_b200.parallel import allreduce_budget, budget_means, divergence_order, shard
+from noahmp_b200.parallel import allreduce_budget, budget_means, divergence_order, gather_columns, shard
 
 
 def test_shard_covers_everything_once():
@@ -119,3 +119,34 @@ def test_budget_allreduce_matches_single_process(oracle_libs):
 def test_allreduce_is_identity_without_process_group():
     b = torch.arange(L.NBUDGET, dtype=torch.float64)
     assert torch.equal(allreduce_budget(b.clone()), b)
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ncol = 301                                                  # uneven: 151 + 150
+    full = torch.arange(5 * ncol, dtype=torch.float32).reshape(5, ncol)
+    c0, n = shard(ncol, rank, world)
+    got = gather_columns(full[:, c0:c0 + n].contiguous(), ncol)
+    q.put((rank, bool(torch.equal(got, full))))
+    dist.destroy_process_group()
+
+
+def test_gather_columns_rebuilds_the_block_partition():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
+    x = torch.ones(3, 7)
+    assert gather_columns(x, 7) is x                            # no process group: identity

@@ -144,6 +144,34 @@ def test_dynamic_vegetation_run_starts_with_a_canopy(tmp_path, tables):
     assert np.isfinite(dg[L.D["NPP"]]).all()
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_file_driven_run(tmp_path, tables):
+    """torchrun, two ranks: each GPU advances its block of columns; gathered outputs and restarts equal the one-GPU run."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from noahmp_b200.driver import read_restart, run_files
+    (tmp_path / "one").mkdir()
+    cfg = _make_case(tmp_path / "one", ncol=101, hours=4)                # uneven shards: 51 + 50 columns
+    ref = run_files(cfg, variant="parity")
+    ref_state, _, _ = read_restart(str(tmp_path / "one" / "restart" / "RESTART.200007010200.npz"))
+    ref_diag = np.load(tmp_path / "one" / "out" / "200007010100.LDASOUT.npz")["diag"]
+    # same inputs, separate output directories
+    nml = (tmp_path / "one" / "case.nml").read_text().replace(f"{tmp_path}/one/out", f"{tmp_path}/two/out") \
+        .replace(f"{tmp_path}/one/restart", f"{tmp_path}/two/restart")
+    (tmp_path / "two").mkdir()
+    (tmp_path / "two" / "case.nml").write_text(nml)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_multi_gpu_driver.py"),
+                        str(tmp_path / "two" / "case.nml")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert f"RANKS 2 STEPS {ref['steps']} FLAGGED 0 COLUMNS 101" in r.stdout
+    st, when, step = read_restart(str(tmp_path / "two" / "restart" / "RESTART.200007010200.npz"))
+    assert step == 16 and np.array_equal(st.view(np.int32), ref_state.view(np.int32))
+    dg = np.load(tmp_path / "two" / "out" / "200007010100.LDASOUT.npz")["diag"]
+    assert np.array_equal(dg.view(np.int32), ref_diag.view(np.int32))
+
+
 def test_main_entry_point_runs_the_synthetic_single_point(tmp_path):
     import importlib.util
     from conftest import ROOT
