@@ -23,7 +23,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["noahmp_abi.cu"]
-HEADERS = ["common.cuh", "energy.cuh", "water.cuh", "column_step.cuh", os.path.join("..", "..", "include", "noahmp_b200.h")]
+HEADERS = ["common.cuh", "energy.cuh", "water.cuh", "column_step.cuh", "forcing_prep.cuh", os.path.join("..", "..", "include", "noahmp_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

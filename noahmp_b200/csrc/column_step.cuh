@@ -108,7 +108,9 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
   const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
 
   DiagSink<DIAG> dg;
-  dg.base = DIAG ? a.diag + ii : nullptr;
+  // only the owner of a column writes its diagnostics: tail threads shadow the last column and a column with a type
+  // outside the tables runs on substitute type 1 just to keep step with its CTA - neither may store (see below)
+  dg.base = (DIAG && active && !badtype) ? a.diag + i : nullptr;
   dg.stride = n;
   unsigned anyflag = badtype ? (unsigned)FLAG_BADTYPE : 0u;
   double b_errwat = 0.0, b_errabs = 0.0, b_errmax = 0.0, b_fsa = 0.0, b_fsr = 0.0, b_fira = 0.0, b_fsh = 0.0, b_lh = 0.0;
@@ -136,7 +138,10 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
     const bool last = (s == a.nsteps - 1);
     DiagSink<DIAG> dgs = dg;
     if (DIAG && !last) dgs.base = nullptr;   // diagnostics of the last step only
-    const float JULIAN = (float)(rc.julian0 + (double)s * (double)DT / 86400.0);
+    // driver duty: day of year, wrapped into [0, YEARLEN) so that a launch may cross 31 December
+    // (phenology's month index IT1 = int(12 JULIAN / YEARLEN + 0.5) must stay in 0..12, func:586-594)
+    const double jd = rc.julian0 + (double)s * (double)DT / 86400.0;
+    const float JULIAN = (float)(jd - (double)rc.yearlen * floor(jd / (double)rc.yearlen));
     unsigned flags = 0;
 
   NMP_PHASE_SYNC_AT(0);
@@ -291,6 +296,10 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
     }
   }
 
+  // a column whose type indices are outside the tables: state untouched, diagnostics zero, only its flag word is set
+  if (DIAG && active && badtype && a.diag != nullptr) {
+    for (int q = 0; q < NDIAG; ++q) a.diag[(int64_t)q * n + i] = (q == D_FLAGS) ? __int_as_float((int)anyflag) : 0.0f;
+  }
   // ---- store the column -----------------------------------------------------------------------------
   if (active && !badtype) {
     float* S = a.state + i;
@@ -310,19 +319,21 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
 
   // ---- budget reduction: warp shuffle, one atomic per warp and quantity --------------------------------
   if (BUDGET) {
-    const double on = (active && !badtype) ? 1.0 : 0.0;
-    const double fin = (active && a.final_launch) ? 1.0 : 0.0;
+    // selects, not products: a flagged column's accumulators may be NaN/Inf (0 x NaN = NaN would poison the domain sums)
+    const bool on = active && !badtype;
+    const bool fin = active && a.final_launch;
+    auto keep = [&](double x) { return (on && isfinite(x)) ? x : 0.0; };
     double soilw = 0.0;
     static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       const float thick = (k == 1) ? -rc.zsoil[0] : (rc.zsoil[k > 1 ? k - 2 : 0] - rc.zsoil[k - 1]);
       soilw += (double)(c.SMC[IX4(k)] * thick * 1000.0f);
     });
     double v[NBUDGET];
-    v[B_NCELL] = fin; v[B_NFLAGGED] = (active && anyflag != 0) ? 1.0 : 0.0; v[B_ERRWAT_SUM] = on * b_errwat;
-    v[B_ERRWAT_ABS] = on * b_errabs; v[B_ERRWAT_MAXABS] = on * b_errmax; v[B_FSA] = on * b_fsa; v[B_FSR] = on * b_fsr;
-    v[B_FIRA] = on * b_fira; v[B_FSH] = on * b_fsh; v[B_LH] = on * b_lh; v[B_SSOIL] = on * b_ssoil;
-    v[B_PRCP_DT] = on * b_prcp; v[B_ET_DT] = on * b_et; v[B_RUNOFF_DT] = on * b_runoff;
-    v[B_SNEQV] = fin * on * (double)c.sneqv; v[B_SOILWATER] = fin * on * soilw;
+    v[B_NCELL] = (fin && on) ? 1.0 : 0.0; v[B_NFLAGGED] = (active && anyflag != 0) ? 1.0 : 0.0; v[B_ERRWAT_SUM] = keep(b_errwat);
+    v[B_ERRWAT_ABS] = keep(b_errabs); v[B_ERRWAT_MAXABS] = keep(b_errmax); v[B_FSA] = keep(b_fsa); v[B_FSR] = keep(b_fsr);
+    v[B_FIRA] = keep(b_fira); v[B_FSH] = keep(b_fsh); v[B_LH] = keep(b_lh); v[B_SSOIL] = keep(b_ssoil);
+    v[B_PRCP_DT] = keep(b_prcp); v[B_ET_DT] = keep(b_et); v[B_RUNOFF_DT] = keep(b_runoff);
+    v[B_SNEQV] = fin ? keep((double)c.sneqv) : 0.0; v[B_SOILWATER] = fin ? keep(soilw) : 0.0;
     static_for<0, (NBUDGET) - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
       const double r = (q == B_ERRWAT_MAXABS) ? warp_max(v[q]) : warp_sum(v[q]);
       if ((threadIdx.x & 31) == 0) {

@@ -1140,8 +1140,11 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
     L.second(iter);
   }
 #else
+#ifndef NMP_EXPERIMENT_NITERC   // timing-only experiments cap the pass count (results wrong): what is the tail worth?
+#define NMP_EXPERIMENT_NITERC 20
+#endif
 #pragma unroll 1
-  for (int iter = 7; iter <= 20; ++iter) {
+  for (int iter = 7; iter <= NMP_EXPERIMENT_NITERC; ++iter) {
     if (!L.running) break;
     L.first(opt, iter);
     L.second(iter);

@@ -29,9 +29,9 @@ struct noahmp_ctx {
   Tables host_tables{};
   Tables* dev_tables = nullptr;
   double* dev_budget_scratch = nullptr;   // NBUDGET doubles
-  // grow-only staging buffers of noahmp_run_host
-  float* h_state = nullptr; float* h_forcing = nullptr; float* h_static_f = nullptr; int* h_static_i = nullptr;
-  float* h_diag = nullptr;
+  // grow-only DEVICE staging buffers of noahmp_run_host
+  float* d_state = nullptr; float* d_forcing = nullptr; float* d_static_f = nullptr; int* d_static_i = nullptr;
+  float* d_diag = nullptr;
   size_t cap_state = 0, cap_forcing = 0, cap_static_f = 0, cap_static_i = 0, cap_diag = 0;
   // noahmp_advance_host: copy stream, double-buffered forcing, hand-off events
   cudaStream_t copy_stream = nullptr;
@@ -192,7 +192,7 @@ int noahmp_finalize(noahmp_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->dev_tables);
   cudaFree(c->dev_budget_scratch);
-  cudaFree(c->h_state); cudaFree(c->h_forcing); cudaFree(c->h_static_f); cudaFree(c->h_static_i); cudaFree(c->h_diag);
+  cudaFree(c->d_state); cudaFree(c->d_forcing); cudaFree(c->d_static_f); cudaFree(c->d_static_i); cudaFree(c->d_diag);
   cudaFree(c->fbuf[0]); cudaFree(c->fbuf[1]);
   for (int k = 0; k < 2; ++k) {
     if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
@@ -259,6 +259,7 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
   if (ncol == 0 || nsteps == 0) return 0;   // empty batch: nothing to do (an empty tensor has a null pointer)
   if (!rp || !state_dev || !forcing_dev || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
   if (!(rp->dt > 0.0f) || rp->yearlen <= 0) return fail(c, -5, "dt and yearlen must be positive");
+  if (!std::isfinite(rp->julian0)) return fail(c, -5, "julian0 must be finite (it is wrapped into [0, yearlen) per step)");
   for (int k = 0; k < 4; ++k)
     if (!(rp->zsoil[k] < (k ? rp->zsoil[k - 1] : 0.0f))) return fail(c, -5, "zsoil must be negative and decreasing");
   CUDA_TRY(c, cudaSetDevice(c->device));
@@ -300,22 +301,22 @@ int64_t noahmp_run_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol
   const bool ext = !c->opt_is_default;
   const size_t nplanes = ext ? NSTATE : NSTATE_CORE;   // the 13 extended planes are dead for the shipped options
   int rc;
-  if ((rc = ensure(c, (void**)&c->h_state, &c->cap_state, sizeof(float) * NSTATE * n))) return rc;
-  if ((rc = ensure(c, (void**)&c->h_forcing, &c->cap_forcing, sizeof(float) * NFORCING * n * (size_t)nsteps))) return rc;
-  if ((rc = ensure(c, (void**)&c->h_static_f, &c->cap_static_f, sizeof(float) * NSTATIC_F * n))) return rc;
-  if ((rc = ensure(c, (void**)&c->h_static_i, &c->cap_static_i, sizeof(int) * n))) return rc;
-  if (diag && (rc = ensure(c, (void**)&c->h_diag, &c->cap_diag, sizeof(float) * NDIAG * n))) return rc;
+  if ((rc = ensure(c, (void**)&c->d_state, &c->cap_state, sizeof(float) * NSTATE * n))) return rc;
+  if ((rc = ensure(c, (void**)&c->d_forcing, &c->cap_forcing, sizeof(float) * NFORCING * n * (size_t)nsteps))) return rc;
+  if ((rc = ensure(c, (void**)&c->d_static_f, &c->cap_static_f, sizeof(float) * NSTATIC_F * n))) return rc;
+  if ((rc = ensure(c, (void**)&c->d_static_i, &c->cap_static_i, sizeof(int) * n))) return rc;
+  if (diag && (rc = ensure(c, (void**)&c->d_diag, &c->cap_diag, sizeof(float) * NDIAG * n))) return rc;
   cudaStream_t st = c->stream;
-  CUDA_TRY(c, cudaMemcpyAsync(c->h_state, state, sizeof(float) * nplanes * n, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(c, cudaMemcpyAsync(c->h_forcing, forcing, sizeof(float) * NFORCING * n * (size_t)nsteps, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(c, cudaMemcpyAsync(c->h_static_f, static_f, sizeof(float) * NSTATIC_F * n, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(c, cudaMemcpyAsync(c->h_static_i, static_i, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_state, state, sizeof(float) * nplanes * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_forcing, forcing, sizeof(float) * NFORCING * n * (size_t)nsteps, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_static_f, static_f, sizeof(float) * NSTATIC_F * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_static_i, static_i, sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(c, cudaMemsetAsync(c->dev_budget_scratch, 0, sizeof(double) * NBUDGET, st));
-  rc = noahmp_run(c, rp, ncol, nsteps, c->h_state, c->h_forcing, (int64_t)NFORCING * ncol, c->h_static_f, c->h_static_i,
-                  diag ? c->h_diag : nullptr, c->dev_budget_scratch);
+  rc = noahmp_run(c, rp, ncol, nsteps, c->d_state, c->d_forcing, (int64_t)NFORCING * ncol, c->d_static_f, c->d_static_i,
+                  diag ? c->d_diag : nullptr, c->dev_budget_scratch);
   if (rc) return rc;
-  CUDA_TRY(c, cudaMemcpyAsync(state, c->h_state, sizeof(float) * nplanes * n, cudaMemcpyDeviceToHost, st));
-  if (diag) CUDA_TRY(c, cudaMemcpyAsync(diag, c->h_diag, sizeof(float) * NDIAG * n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaMemcpyAsync(state, c->d_state, sizeof(float) * nplanes * n, cudaMemcpyDeviceToHost, st));
+  if (diag) CUDA_TRY(c, cudaMemcpyAsync(diag, c->d_diag, sizeof(float) * NDIAG * n, cudaMemcpyDeviceToHost, st));
   double b[NBUDGET];
   CUDA_TRY(c, cudaMemcpyAsync(b, c->dev_budget_scratch, sizeof(double) * NBUDGET, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(c, cudaStreamSynchronize(st));

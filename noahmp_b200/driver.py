@@ -203,7 +203,11 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
     t, step0 = cfg.begdatetime, 0
     res_path = cfg.resfile if os.path.isabs(str(cfg.resfile)) else os.path.join(cfg.resdir, str(cfg.resfile))
     if os.path.isfile(res_path):
-        cols.state, t, step0 = read_restart(res_path)
+        rst, t, step0 = read_restart(res_path)
+        if rst.shape != cols.state.shape:
+            raise ValueError(f"ERR: restart {res_path} holds {rst.shape[1]} columns x {rst.shape[0]} planes, the initialization "
+                             f"file {cfg.initfile} describes {cols.ncol} columns x {cols.state.shape[0]} planes")
+        cols.state = rst
     dtm = cfg.timestep
     out_freq, res_freq = F.parse_frequency(cfg.outfreq), F.parse_frequency(cfg.resfreq)
     eng = NoahMP(tables, cfg.physics_options(), device=device, fast=variant)
@@ -216,6 +220,7 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
     geo = torch.from_numpy(np.ascontiguousarray(F.geo_planes(cols.lat, cols.lon)[:, mine])).to(dev)
     diag = torch.zeros((L.NDIAG, ncol), dtype=torch.float32, device=dev)
     budget = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
+    end_slots = torch.tensor([L.B["NCELL"], L.B["SNEQV"], L.B["SOILWATER"]], device=dev)
     forcing = torch.empty((max_steps_per_launch, L.NFORCING, ncol), dtype=torch.float32, device=dev)
     reader = F.RecordReader(cfg.indir, cfg.infreq, cfg.begdatetime, ntot, dev)
     rec = (lambda when: reader.record(when)[:, mine].contiguous()) if world > 1 else reader.record
@@ -230,6 +235,7 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
             if F.is_boundary(t, cfg.begdatetime, out_freq) or F.is_boundary(t, cfg.begdatetime, res_freq):
                 break
         rp = eng.run_params(dtm.total_seconds(), synth.ZSOIL, F.julian_of(t_launch), F.yearlen_of(t_launch))
+        budget[end_slots] = 0.0   # NCELL / SNEQV / SOILWATER are end-of-launch snapshots: keep the last launch's only
         eng.run(rp, state, forcing[:g], sf, si, diag, budget)
         nsteps += g
         if F.is_boundary(t, cfg.begdatetime, out_freq):
@@ -309,11 +315,14 @@ def run_case(cfg, ncol: int = 1, chunk: int = 96, device: int = 0, variant="fast
     static_i = torch.from_numpy(w.static_i).to(dev)
     diag = torch.zeros((L.NDIAG, ncol), dtype=torch.float32, device=dev)
     budget = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
+    end_slots = torch.tensor([L.B["NCELL"], L.B["SNEQV"], L.B["SOILWATER"]], device=dev)
     done = 0
     while done < nsteps:  # forcing is produced chunk by chunk, state stays on the device
         n = min(chunk, nsteps - done)
         fo = np.stack([synth.forcing_step(w, done + s) for s in range(n)])
-        rp = eng.run_params(w.dt, synth.ZSOIL, w.julian0 + done * w.dt / 86400.0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
+        t_chunk = cfg.begdatetime + dt.timedelta(seconds=done * w.dt)   # calendar date of the chunk: JULIAN / YEARLEN follow it
+        rp = eng.run_params(w.dt, synth.ZSOIL, F.julian_of(t_chunk), F.yearlen_of(t_chunk), w.zref, w.co2_frac, w.o2_frac, w.foln)
+        budget[end_slots] = 0.0
         eng.run(rp, state, torch.from_numpy(fo).to(dev), static_f, static_i, diag, budget)
         done += n
     torch.cuda.synchronize()

@@ -105,8 +105,11 @@ class RecordReader:
         n = self.freq[0]
         k = int((t - self.origin).total_seconds() // n)
         t0 = self.origin + dt.timedelta(seconds=k * n)
-        t1 = t0 + dt.timedelta(seconds=n)
-        return t0, t1, (t - t0).total_seconds() / n
+        w = (t - t0).total_seconds() / n
+        # on a record time the weight is 0 and the later record is not needed: return t0 twice, so that the last step of
+        # a run does not ask for a record dated after the end of the forcing period
+        t1 = t0 if w == 0.0 else t0 + dt.timedelta(seconds=n)
+        return t0, t1, w
 
     def record(self, t: dt.datetime):
         import torch

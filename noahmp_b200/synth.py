@@ -3,7 +3,7 @@
 The reference ships no forcing, no ``init.nc`` and no driver (``run/main.py:12-14`` only prints the
 config), so the workloads are generated.  The per-step forcing generator is a counter-based integer
 hash followed by +,-,*,/ only, with every transcendental evaluated once per step on the host
-(:func:`step_scalars`); the same arithmetic is implemented on the device (``csrc/forcing_synth.cu``),
+(:func:`step_scalars`); the same arithmetic is implemented on the device (``synth_forcing_kernel`` in ``csrc/noahmp_abi.cu``),
 so host and device forcing are bit-identical and the CPU oracle and the CUDA kernel can be fed the
 same numbers at any size.
 

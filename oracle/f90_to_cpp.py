@@ -1139,7 +1139,8 @@ def native_driver(tr, sub):
     for k, nm in enumerate(NATIVE_FORCING):
         e(f"      {nm} = forcing[((size_t)s * {len(NATIVE_FORCING)} + fp[{k}]) * ncol + i];")
     e("      psfc = sfcprs; co2air = rp->co2_frac * sfcprs; o2air = rp->o2_frac * sfcprs;")
-    e("      julian = (float)(rp->julian0 + (double)s * (double)rp->dt / 86400.0);")
+    e("      { const double jd = rp->julian0 + (double)s * (double)rp->dt / 86400.0, yl = (double)rp->yearlen;")
+    e("        julian = (float)(jd - yl * floor(jd / yl)); }")
     e(f"      for (int k = -2; k <= 0; ++k) ficeold[k + 2] = (k >= isnow + 1) ? snice[k + 2] / (snice[k + 2] + snliq[k + 2]) : ({REAL})0;")
     e("      try {")
     e(f"        noahmp_sflx({', '.join(cname(a) for a in sub.args)});")

@@ -192,7 +192,8 @@ class RefModel:
                            q2=f[L.F["Q2"]], soldn=f[L.F["SOLDN"]], lwdn=f[L.F["LWDN"]], prcp=f[L.F["PRCP"]], cosz=f[L.F["COSZ"]])
                 col["co2air"] = f32(co2_frac) * f32(col["sfcprs"])
                 col["o2air"] = f32(o2_frac) * f32(col["sfcprs"])
-                col["julian"] = f32(np.float64(julian0) + np.float64(s) * np.float64(f32(dt)) / 86400.0)
+                jd = np.float64(julian0) + np.float64(s) * np.float64(f32(dt)) / 86400.0
+                col["julian"] = f32(jd - np.float64(yearlen) * np.floor(jd / np.float64(yearlen)))
                 fice = np.zeros(3, f32)
                 for k in (-2, -1, 0):
                     if k >= col["isnow"] + 1:

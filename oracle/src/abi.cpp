@@ -182,7 +182,10 @@ long long oracle_run(oracle_ctx* c, const RunParams* rp, long long ncol, int nst
       col.PSFC = col.SFCPRS;                          // offline: lowest-model-level pressure = surface
       col.CO2AIR = rp->co2_frac * col.SFCPRS;
       col.O2AIR = rp->o2_frac * col.SFCPRS;
-      col.JULIAN = (float)(rp->julian0 + (double)s * (double)rp->dt / 86400.0);
+      {  // driver duty: day of year wrapped into [0, YEARLEN) (a launch may cross 31 December)
+        const double jd = rp->julian0 + (double)s * (double)rp->dt / 86400.0, yl = (double)rp->yearlen;
+        col.JULIAN = (float)(jd - yl * floor(jd / yl));
+      }
       // FICEOLD: ice fraction of the snow layers at the start of the step (driver duty)
       for (int k = -2; k <= 0; ++k) {
         if (k >= col.ISNOW + 1) col.FICEOLD(k) = col.SNICE(k) / (col.SNICE(k) + col.SNLIQ(k));

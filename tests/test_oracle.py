@@ -198,3 +198,23 @@ def test_empty_and_zero_step_batches(tables, oracle_libs):
     assert o.run(w.state, np.zeros((0, L.NFORCING, 8), f32), w.static_f, w.static_i, dt=w.dt, zsoil=synth.ZSOIL,
                  julian0=0.0, yearlen=365) == 0
     assert np.array_equal(before.view(np.int32), w.state.view(np.int32))
+
+
+def test_launch_across_the_year_boundary(orc):
+    """Driver duty: JULIAN is wrapped into [0, YEARLEN) per step, so a launch that starts on 31 December and runs into
+    January sees January's month weights (phenology, func:580-597), not table slots past December.  One 48-step launch
+    from day 364.0 must equal a 24-step launch from 364.0 followed by a 24-step launch from 0.0, bit for bit, and must
+    differ from a run that is (wrongly) kept in late December for its second day."""
+    w = synth.make_workload("global025", ncol=256, nsteps=48)
+    f = synth.forcing_all(w)
+    kw = dict(dt=w.dt, zsoil=synth.ZSOIL, yearlen=365, zref=w.zref, co2_frac=w.co2_frac, o2_frac=w.o2_frac, foln=w.foln)
+    one = w.state.copy()
+    assert orc.run(one, f, w.static_f, w.static_i, julian0=364.0, **kw) == 0
+    two = w.state.copy()
+    orc.run(two, np.ascontiguousarray(f[:24]), w.static_f, w.static_i, julian0=364.0, **kw)
+    orc.run(two, np.ascontiguousarray(f[24:]), w.static_f, w.static_i, julian0=0.0, **kw)
+    assert np.array_equal(one.view(np.int32), two.view(np.int32))
+    dec = w.state.copy()
+    orc.run(dec, np.ascontiguousarray(f[:24]), w.static_f, w.static_i, julian0=364.0, **kw)
+    orc.run(dec, np.ascontiguousarray(f[24:]), w.static_f, w.static_i, julian0=363.0, **kw)
+    assert not np.array_equal(one.view(np.int32), dec.view(np.int32))

