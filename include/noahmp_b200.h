@@ -27,7 +27,7 @@ typedef struct noahmp_ctx noahmp_ctx;
 #define NOAHMP_NSTATE_CORE 44
 #define NOAHMP_NFORCING     9  /* SFCTMP SFCPRS UU VV Q2 SOLDN LWDN PRCP COSZ  (func:72-74)        */
 #define NOAHMP_NSTATIC_F    4  /* LAT SHDFAC TBOT SHDMAX                                           */
-#define NOAHMP_NDIAG       63  /* 58 outputs of func:82-91 + ERRWAT ERRSW ERRENG ITER FLAGS        */
+#define NOAHMP_NDIAG       69  /* 58 outputs of func:82-91 + ERRWAT ERRSW ERRENG ITER FLAGS + 6 accumulations */
 #define NOAHMP_NBUDGET     16
 #define NOAHMP_NGEN        53
 #define NOAHMP_NSOILP      10
@@ -89,7 +89,11 @@ int noahmp_set_tables(noahmp_ctx* ctx, const float* gen, int ngen, const float* 
  *   forcing_dev  step s at forcing_dev + s*forcing_step_stride, each [NFORCING][ncol]
  *   static_f_dev [NSTATIC_F][ncol]; static_i_dev [ncol] packed types:
  *                lutyp | sltyp<<8 | slptyp<<16 | ISC<<24 | (IST-1)<<28 | ICE<<29
- *   diag_dev     [NDIAG][ncol] values of the LAST step, or NULL
+ *   diag_dev     [NDIAG][ncol] or NULL: planes 0..62 hold the values of the LAST step; planes 63..68 (ACCPRCP ACCECAN
+ *                ACCETRAN ACCEDIR SFCRNOFF UGDRNOFF, mm) are accumulations - every step's precipitation, canopy
+ *                evaporation, transpiration, ground evaporation, surface and subsurface runoff x dt is ADDED to what
+ *                the plane holds, so they run across launches until the caller zeroes them (output cadence,
+ *                offline/noahmp_config.py:83-84 output_frequency)
  *   budget_dev   [NBUDGET] fp64 sums accumulated (+=) over all columns and steps, or NULL          */
 int noahmp_run(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
                const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,

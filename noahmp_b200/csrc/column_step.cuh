@@ -113,6 +113,10 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
   dg.base = (DIAG && active && !badtype) ? a.diag + i : nullptr;
   dg.stride = n;
   unsigned anyflag = badtype ? (unsigned)FLAG_BADTYPE : 0u;
+  float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // ACCPRCP ACCECAN ACCETRAN ACCEDIR SFCRNOFF UGDRNOFF (DIAG builds)
+  if (DIAG && dg.base != nullptr) {
+    static_for<0, 5>([&](auto q_) { constexpr int q = decltype(q_)::value; acc[q] = dg.base[(int64_t)(D_ACCPRCP + q) * n]; });
+  }
   double b_errwat = 0.0, b_errabs = 0.0, b_errmax = 0.0, b_fsa = 0.0, b_fsr = 0.0, b_fira = 0.0, b_fsh = 0.0, b_lh = 0.0;
   double b_ssoil = 0.0, b_prcp = 0.0, b_et = 0.0, b_runoff = 0.0;
 
@@ -288,6 +292,10 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
                            ((w.niter_soil & 0xff) << 24));
       dgs.puti(D_FLAGS, (int)anyflag);
     }
+    if (DIAG) {   // accumulations between outputs (driver duty; offline/noahmp_config.py:83-84)
+      acc[0] = acc[0] + f.PRCP * DT; acc[1] = acc[1] + w.ECAN * DT; acc[2] = acc[2] + w.ETRAN * DT;
+      acc[3] = acc[3] + EDIR * DT; acc[4] = acc[4] + w.runsrf * DT; acc[5] = acc[5] + w.runsub * DT;
+    }
     if (BUDGET) {
       b_errwat += (double)ERRWAT; b_errabs += fabs((double)ERRWAT); b_errmax = fmax(b_errmax, fabs((double)ERRWAT));
       b_fsa += (double)e.FSA; b_fsr += (double)e.FSR; b_fira += (double)e.FIRA; b_fsh += (double)e.FSH;
@@ -296,6 +304,9 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
     }
   }
 
+  if (DIAG && dg.base != nullptr) {
+    static_for<0, 5>([&](auto q_) { constexpr int q = decltype(q_)::value; dg.base[(int64_t)(D_ACCPRCP + q) * n] = acc[q]; });
+  }
   // a column whose type indices are outside the tables: state untouched, diagnostics zero, only its flag word is set
   if (DIAG && active && badtype && a.diag != nullptr) {
     for (int q = 0; q < NDIAG; ++q) a.diag[(int64_t)q * n + i] = (q == D_FLAGS) ? __int_as_float((int)anyflag) : 0.0f;

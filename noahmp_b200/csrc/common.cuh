@@ -50,7 +50,9 @@ enum {
   D_T2MV, D_T2MB, D_Q2V, D_Q2B, D_RUNSRF, D_RUNSUB, D_APAR, D_PSN, D_SAV, D_SAG, D_FSNO, D_NEE, D_GPP, D_NPP,
   D_FVEG, D_ALBEDO, D_QSNBOT, D_PONDING, D_PONDING1, D_PONDING2, D_RSSUN, D_RSSHA, D_BGAP, D_WGAP, D_CHV, D_CHB,
   D_EMISSI, D_SHG, D_SHC, D_SHB, D_EVG, D_EVB, D_GHV, D_GHB, D_IRG, D_IRC, D_IRB, D_TR, D_EVC, D_CHLEAF, D_CHUC,
-  D_CHV2, D_CHB2, D_FPICE, D_ERRWAT, D_ERRSW, D_ERRENG, D_ITER, D_FLAGS, NDIAG = 63
+  D_CHV2, D_CHB2, D_FPICE, D_ERRWAT, D_ERRSW, D_ERRENG, D_ITER, D_FLAGS,
+  // accumulated over every step since the caller last zeroed them (mm): the planes are read, added to and written back
+  D_ACCPRCP = 63, D_ACCECAN, D_ACCETRAN, D_ACCEDIR, D_SFCRNOFF, D_UGDRNOFF, NDIAG = 69
 };
 enum {
   B_NCELL = 0, B_NFLAGGED, B_ERRWAT_SUM, B_ERRWAT_ABS, B_ERRWAT_MAXABS, B_FSA, B_FSR, B_FIRA, B_FSH, B_LH, B_SSOIL,

@@ -56,7 +56,7 @@ const char* kDiagNames[NDIAG] = {
     "T2MB", "Q2V", "Q2B", "RUNSRF", "RUNSUB", "APAR", "PSN", "SAV", "SAG", "FSNO", "NEE", "GPP", "NPP", "FVEG", "ALBEDO",
     "QSNBOT", "PONDING", "PONDING1", "PONDING2", "RSSUN", "RSSHA", "BGAP", "WGAP", "CHV", "CHB", "EMISSI", "SHG", "SHC",
     "SHB", "EVG", "EVB", "GHV", "GHB", "IRG", "IRC", "IRB", "TR", "EVC", "CHLEAF", "CHUC", "CHV2", "CHB2", "FPICE",
-    "ERRWAT", "ERRSW", "ERRENG", "ITER", "FLAGS"};
+    "ERRWAT", "ERRSW", "ERRENG", "ITER", "FLAGS", "ACCPRCP", "ACCECAN", "ACCETRAN", "ACCEDIR", "SFCRNOFF", "UGDRNOFF"};
 const char* kBudgetNames[NBUDGET] = {"NCELL", "NFLAGGED", "ERRWAT_SUM", "ERRWAT_ABS", "ERRWAT_MAXABS", "FSA", "FSR",
                                      "FIRA", "FSH", "LH", "SSOIL", "PRCP_DT", "ET_DT", "RUNOFF_DT", "SNEQV", "SOILWATER"};
 
@@ -312,6 +312,8 @@ int64_t noahmp_run_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol
   CUDA_TRY(c, cudaMemcpyAsync(c->d_static_f, static_f, sizeof(float) * NSTATIC_F * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(c, cudaMemcpyAsync(c->d_static_i, static_i, sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(c, cudaMemsetAsync(c->dev_budget_scratch, 0, sizeof(double) * NBUDGET, st));
+  // the accumulation planes of a host call cover this call: start them at zero
+  if (diag) CUDA_TRY(c, cudaMemsetAsync(c->d_diag + (size_t)D_ACCPRCP * n, 0, sizeof(float) * (NDIAG - D_ACCPRCP) * n, st));
   rc = noahmp_run(c, rp, ncol, nsteps, c->d_state, c->d_forcing, (int64_t)NFORCING * ncol, c->d_static_f, c->d_static_i,
                   diag ? c->d_diag : nullptr, c->dev_budget_scratch);
   if (rc) return rc;

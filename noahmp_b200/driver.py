@@ -104,9 +104,58 @@ def initial_vegetation(tables: ParamTables, lutyp, lat_rad, when: dt.datetime | 
     return {k: np.where(bare, f32(0.0), v).astype(f32) for k, v in pools.items()}
 
 
-def columns_from_init(path: str, tables: ParamTables, when: dt.datetime | None = None, static_path: str | None = None) -> Columns:
+def equilibrium_water_table(tables: ParamTables, sltyp, smc4, sh2o4, timean=None, zsoil=synth.ZSOIL, zwt_max: float = 25.0):
+    """Initial water-table depth ZWT [m] and aquifer storage WA = WT [mm] of the SIMGM groundwater scheme (opt_run = 1) at
+    which recharge equals discharge for the initial moisture of the bottom soil layer - the state ``groundwater``
+    (func:6458-6639) neither fills nor drains.  The reference has no initialisation code (upstream WRF's
+    NOAHMP_INIT sets the constants WA = 4900 mm, ZWT = 2.5 m); this is the specification used here, in the reference's own
+    terms, for a water table below the soil column (IWT = NSOIL, func:6545-6551):
+
+      QDIS(z) = (1 - FCRMAX) RSBMX exp(-TIMEAN) exp(-FFF (z - 2))                        func:6557 (RSBMX 5, FFF 6)
+      QIN(z)  = KA (1 + SMPFZ / (1000 (z - ZNODE4)))                                      func:6566-6570 rearranged
+      KA = 1000 DKSAT max(.01, SMC4/SMCMAX)^(2b+3) (1 - FCR4)                             func:6413-6415 (wdfcnd1)
+      SMPFZ = max(-120000, CMIC (-PSISAT 1000 S^-b)), S = clip(SMC4/SMCMAX, .01, 1)       func:6560-6563 (CMIC 0.2)
+      FCR = max(0, exp(-A (1 - FICE)) - exp(-A)) / (1 - exp(-A)), A = 4, FICE = min(1, ice/SMCMAX)     func:5900-5904
+
+    QIN - QDIS increases with z, so the root on [2, zwt_max] is unique; it is found by 60 bisections in fp64, and taken at
+    the interval end when there is no sign change (2.0 m is where WA reaches its cap of 5000 mm, func:6584).  WA follows
+    from the scheme's own relation ZWT = (-ZSOIL(4) + 25) - WA / 1000 / ROUS (func:6579), ROUS = 0.2, so that the first call of
+    ``groundwater`` does not jump: 1.5 m <= ZWT (func:6609) and WA <= 5000 mm hold by construction."""
+    sl = np.asarray(sltyp, np.int64) - 1
+    g = lambda k: np.asarray(tables.soil[k], np.float64)[sl]  # noqa: E731
+    smcmax, bexp, psisat, dksat = g("SMCMAX"), g("BEXP"), g("PSISAT"), g("DKSAT")
+    smc4, sh2o4 = np.asarray(smc4, np.float64), np.asarray(sh2o4, np.float64)
+    timean = float(tables.gen["TIMEAN"]) if timean is None else float(timean)
+    a = 4.0
+    fice = np.minimum(1.0, np.maximum(smc4 - sh2o4, 0.0) / smcmax)
+    fcr = np.maximum(0.0, np.exp(-a * (1.0 - fice)) - np.exp(-a)) / (1.0 - np.exp(-a))
+    sat = np.clip(smc4 / smcmax, 0.01, 1.0)
+    ka = 1.0e3 * dksat * sat ** (2.0 * bexp + 3.0) * (1.0 - fcr)
+    smpfz = np.maximum(-120000.0, 0.2 * (-psisat * 1000.0 * sat ** (-bexp)))
+    znode4 = -zsoil[2] + 0.5 * (zsoil[2] - zsoil[3])
+    qdis0 = (1.0 - fcr) * 5.0 * np.exp(-timean)
+
+    def excess(z):
+        return ka * (1.0 + smpfz / (1000.0 * (z - znode4))) - qdis0 * np.exp(-6.0 * (z - 2.0))
+
+    lo = np.full(smc4.shape, -float(zsoil[3]), np.float64)
+    hi = np.full(smc4.shape, float(zwt_max), np.float64)
+    flo, fhi = excess(lo), excess(hi)
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        up = excess(mid) < 0.0      # discharge still larger: the balance point is deeper
+        lo = np.where(up, mid, lo)
+        hi = np.where(up, hi, mid)
+    zwt = 0.5 * (lo + hi)
+    zwt = np.where(flo >= 0.0, -float(zsoil[3]), np.where(fhi <= 0.0, float(zwt_max), zwt))
+    wa = ((-float(zsoil[3]) + 25.0) - zwt) * 1000.0 * 0.2
+    return zwt.astype(f32), np.minimum(wa, 5000.0).astype(f32)
+
+
+def columns_from_init(path: str, tables: ParamTables, when: dt.datetime | None = None, static_path: str | None = None,
+                      water_table: str = "equilibrium") -> Columns:
     """``.npz`` keys: lat, lon [deg]; lutyp, sltyp, slptyp, isc (ints); shdfac, tbot; tsk (skin T), stc[4], smc[4],
-    optional sh2o[4], snowh [m], sneqv [mm], canliq, zwt, wa.  A NetCDF-3 file with the HRLDAS / WRF variable names
+    optional sh2o[4], snowh [m], sneqv [mm], canliq, zwt, wa (both absent: :func:`equilibrium_water_table`).  A NetCDF-3 file with the HRLDAS / WRF variable names
     (``ncio.INIT_ALIASES``) is accepted as well; its grid is flattened row-major."""
     z = ncio.read_init(path, static_path) if ncio.is_netcdf(path) else np.load(path)
     n = z["lat"].size
@@ -139,8 +188,15 @@ def columns_from_init(path: str, tables: ParamTables, when: dt.datetime | None =
     st[S["EAH"]] = get("eah", 2000.0)
     st[S["ALBOLD"]] = 0.65
     st[S["CANLIQ"]] = get("canliq", 0.0)
-    st[S["ZWT"]] = get("zwt", 2.5)
-    st[S["WA"]] = get("wa", 4900.0)
+    # water table / aquifer: from the file when it carries them, else the equilibrium of the SIMGM scheme for the initial
+    # bottom-layer moisture (``water_table="constant"`` keeps upstream's 2.5 m / 4900 mm)
+    if "zwt" in z.files and "wa" in z.files:
+        st[S["ZWT"]], st[S["WA"]] = z["zwt"].astype(f32), z["wa"].astype(f32)
+    elif water_table == "equilibrium":
+        st[S["ZWT"]], st[S["WA"]] = equilibrium_water_table(tables, sl, st[L.smc(4)], st[L.soilwat(4)])
+    else:
+        st[S["ZWT"]] = get("zwt", 2.5)
+        st[S["WA"]] = get("wa", 4900.0)
     st[S["WT"]] = st[S["WA"]]
     st[S["CM"]] = 0.1
     st[S["CH"]] = 0.1
@@ -251,6 +307,7 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
                 else:
                     np.savez(p, diag=full, planes=np.asarray(L.DIAG), time=F.stamp(t))
             written.append(p)
+            diag[L.ACC_DIAG_PLANES[0]:] = 0.0   # ACCPRCP ... UGDRNOFF accumulate from one output to the next
         if F.is_boundary(t, cfg.begdatetime, res_freq):
             full = gather_columns(state, ntot).cpu().numpy()
             if as_nc:

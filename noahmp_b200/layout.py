@@ -67,8 +67,11 @@ DIAG = ["FSA", "FSR", "FIRA", "FSH", "SSOIL", "FCEV", "FGEV", "FCTR", "ECAN", "E
         "NEE", "GPP", "NPP", "FVEG", "ALBEDO", "QSNBOT", "PONDING", "PONDING1", "PONDING2", "RSSUN",
         "RSSHA", "BGAP", "WGAP", "CHV", "CHB", "EMISSI", "SHG", "SHC", "SHB", "EVG", "EVB", "GHV", "GHB",
         "IRG", "IRC", "IRB", "TR", "EVC", "CHLEAF", "CHUC", "CHV2", "CHB2", "FPICE",
-        "ERRWAT", "ERRSW", "ERRENG", "ITER", "FLAGS"]
-NDIAG = len(DIAG)  # 63
+        "ERRWAT", "ERRSW", "ERRENG", "ITER", "FLAGS",
+        # accumulated since last zeroed by the caller (mm), HRLDAS names: read-modify-write planes
+        "ACCPRCP", "ACCECAN", "ACCETRAN", "ACCEDIR", "SFCRNOFF", "UGDRNOFF"]
+NDIAG = len(DIAG)  # 69
+ACC_DIAG_PLANES = list(range(63, 69))
 D = {n: i for i, n in enumerate(DIAG)}
 INT_DIAG_PLANES = [D["ITER"], D["FLAGS"]]
 

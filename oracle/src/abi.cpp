@@ -173,6 +173,8 @@ long long oracle_run(oracle_ctx* c, const RunParams* rp, long long ncol, int nst
     col.STBLCP = S(S_STBLCP); col.FASTCP = S(S_FASTCP); col.LAI = S(S_LAI); col.SAI = S(S_SAI);
 
     uint32_t anyflag = 0;
+    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // accumulations between outputs (driver duty)
+    if (diag) for (int q = 0; q < 6; ++q) acc[q] = diag[(size_t)(D_ACCPRCP + q) * ncol + i];
     for (int s = 0; s < nsteps; ++s) {
       const float* f = forcing + ((size_t)s * NFORCING) * ncol + i;
       col.SFCTMP = f[(size_t)F_SFCTMP * ncol]; col.SFCPRS = f[(size_t)F_SFCPRS * ncol];
@@ -193,6 +195,8 @@ long long oracle_run(oracle_ctx* c, const RunParams* rp, long long ncol, int nst
       }
       noahmp_sflx(cx, col);
       anyflag |= col.flags;
+      acc[0] = acc[0] + col.PRCP * rp->dt; acc[1] = acc[1] + col.ECAN * rp->dt; acc[2] = acc[2] + col.ETRAN * rp->dt;
+      acc[3] = acc[3] + col.EDIR * rp->dt; acc[4] = acc[4] + col.runsrf * rp->dt; acc[5] = acc[5] + col.runsub * rp->dt;
     }
     if (anyflag) nflag += 1;
 
@@ -216,6 +220,7 @@ long long oracle_run(oracle_ctx* c, const RunParams* rp, long long ncol, int nst
       D(D_ITER) = i2f((col.iter_vege & 0xff) | ((col.iter_stom_sun & 0xff) << 8) |
                       ((col.iter_stom_sha & 0xff) << 16) | ((col.niter_soil & 0xff) << 24));
       D(D_FLAGS) = i2f((int)anyflag);
+      for (int q = 0; q < 6; ++q) D(D_ACCPRCP + q) = acc[q];
     }
   }
   return nflag;

@@ -42,7 +42,9 @@ enum DiagPlane {
   D_ERRWAT = 58, D_ERRSW, D_ERRENG,
   D_ITER = 61,   // int32 bits: iter_vege | stom_sun<<8 | stom_sha<<16 | niter_soil<<24
   D_FLAGS = 62,  // uint32 bits
-  NDIAG = 63
+  // accumulated over every step since the caller last zeroed them (mm); read-modify-write (driver duty, not func:)
+  D_ACCPRCP = 63, D_ACCECAN, D_ACCETRAN, D_ACCEDIR, D_SFCRNOFF, D_UGDRNOFF,
+  NDIAG = 69
 };
 
 // packed parameter tables (see noahmp_b200/tables.py: pack_tables)

@@ -235,3 +235,67 @@ def test_initial_vegetation_pools(tables):
     assert np.isclose(v["LFMASS"][6], v["LAI"][6] * 1000.0 / max(sla[10], 1.0), rtol=1e-6)
     assert np.isclose(v["STMASS"][7], v["SAI"][7] * 1000.0 / 3.0, rtol=1e-6) and v["WOOD"][7] == 500.0 and v["FASTCP"][7] == 1000.0
     assert (v["SAI"][4:] >= np.maximum(np.float32(0.1) * v["LAI"][4:], np.float32(0.05)) - 1e-7).all()
+
+
+# ---- equilibrium water table / aquifer initialisation ---------------------------------------------
+def test_equilibrium_water_table_invariants_and_no_drift(tmp_path, tables, oracle_libs):
+    """`driver.equilibrium_water_table`: the SIMGM state in which recharge equals discharge for the initial bottom-layer
+    moisture.  Invariants of the scheme hold by construction (ZWT >= 1.5 m func:6609, WA <= 5000 mm func:6584, the
+    ZWT <-> WA relation of func:6579), the residual QIN - QDIS vanishes where the root is interior, and in a spin without
+    precipitation the aquifer of the equilibrium start drifts an order of magnitude less over the first 24 steps than the
+    constants upstream initialises with (2.5 m / 4900 mm).  The physics is the CPU oracle's (the checker)."""
+    from noahmp_b200 import synth
+    from noahmp_b200.driver import columns_from_init, equilibrium_water_table
+    from oracle.oracle import Oracle
+    n = 384
+    init = _init_dict(n)
+    init["snowh"][:] = 0.0
+    init["sneqv"][:] = 0.0
+    np.savez(tmp_path / "init.npz", **init)
+    eq = columns_from_init(str(tmp_path / "init.npz"), tables)
+    const = columns_from_init(str(tmp_path / "init.npz"), tables, water_table="constant")
+    S = L.S
+    assert (const.state[S["ZWT"]] == 2.5).all() and (const.state[S["WA"]] == 4900.0).all()
+    zwt, wa = eq.state[S["ZWT"]], eq.state[S["WA"]]
+    assert (zwt >= 2.0).all() and (zwt <= 25.0).all() and (wa <= 5000.0).all() and (wa >= 400.0 - 1e-3).all()
+    assert np.array_equal(eq.state[S["WT"]], wa)
+    assert np.allclose(zwt, 27.0 - wa.astype(np.float64) / 200.0, atol=2e-4)
+    # a file that carries both fields is taken at its word
+    np.savez(tmp_path / "init2.npz", zwt=np.full(n, 3.0, np.float32), wa=np.full(n, 4800.0, np.float32), **init)
+    given = columns_from_init(str(tmp_path / "init2.npz"), tables)
+    assert (given.state[S["ZWT"]] == 3.0).all() and (given.state[S["WA"]] == 4800.0).all()
+    # residual of the balance where the root is interior (fp64 re-evaluation of the documented formulas)
+    sl = (eq.static_i >> 8) & 0xff
+    g = lambda k: np.asarray(tables.soil[k], np.float64)[sl - 1]  # noqa: E731
+    smc4 = eq.state[L.smc(4)].astype(np.float64)
+    sat = np.clip(smc4 / g("SMCMAX"), 0.01, 1.0)
+    ka = 1e3 * g("DKSAT") * sat ** (2 * g("BEXP") + 3)
+    smp = np.maximum(-120000.0, 0.2 * (-g("PSISAT") * 1000.0 * sat ** (-g("BEXP"))))
+    z = zwt.astype(np.float64)
+    qin = ka * (1.0 + smp / (1000.0 * (z - 1.5)))
+    qdis = 5.0 * np.exp(-float(tables.gen["TIMEAN"])) * np.exp(-6.0 * (z - 2.0))
+    interior = (z > 2.0 + 1e-4) & (z < 25.0 - 1e-4)
+    assert interior.sum() > n // 4
+    assert (np.abs(qin - qdis)[interior] <= 1e-5 * np.maximum(qdis, np.abs(qin))[interior] + 1e-12).all()
+    # no-precipitation spin: 24 hourly steps, night (no evaporative demand), mild air
+    forcing = np.zeros((24, L.NFORCING, n), np.float32)
+    forcing[:, L.F["SFCTMP"]] = eq.state[S["TG"]]
+    forcing[:, L.F["SFCPRS"]] = 95000.0
+    forcing[:, L.F["UU"]] = 2.0
+    forcing[:, L.F["Q2"]] = 0.004
+    forcing[:, L.F["LWDN"]] = 5.67e-8 * eq.state[S["TG"]].astype(np.float64) ** 4 * 0.85
+    forcing[:, L.F["COSZ"]] = -0.5
+    drift = {}
+    for name, cols in (("equilibrium", eq), ("constant", const)):
+        st = cols.state.copy()
+        nflag = Oracle(tables, synth.DEFAULT_OPTS).run(st, forcing, cols.static_f, cols.static_i, dt=3600.0, zsoil=synth.ZSOIL,
+                                                       julian0=180.0, yearlen=365)
+        assert nflag == 0
+        assert (st[S["ZWT"]] >= 1.5).all() and (st[S["WA"]] <= 5000.0).all()
+        drift[name] = np.abs(st[S["WA"]].astype(np.float64) - cols.state[S["WA"]])
+    m = interior
+    assert np.median(drift["equilibrium"][m]) <= 0.1 * np.median(drift["constant"][m]), (np.median(drift["equilibrium"][m]),
+                                                                                      np.median(drift["constant"][m]))
+    print("WA drift over 24 steps [mm], median / p95: equilibrium", np.median(drift["equilibrium"][m]), np.quantile(drift["equilibrium"][m], 0.95),
+          " constant", np.median(drift["constant"][m]), np.quantile(drift["constant"][m], 0.95))
+    assert np.quantile(drift["equilibrium"][m], 0.95) <= 0.25 * np.quantile(drift["constant"][m], 0.95)

@@ -218,3 +218,32 @@ def test_launch_across_the_year_boundary(orc):
     orc.run(dec, np.ascontiguousarray(f[:24]), w.static_f, w.static_i, julian0=364.0, **kw)
     orc.run(dec, np.ascontiguousarray(f[24:]), w.static_f, w.static_i, julian0=363.0, **kw)
     assert not np.array_equal(one.view(np.int32), dec.view(np.int32))
+
+
+def test_accumulated_diagnostics_run_across_launches(orc):
+    """Planes ACCPRCP ... UGDRNOFF (driver duty, offline/noahmp_config.py:83-84): every step adds its flux x dt to what the
+    plane holds, so two launches of 12 steps leave what one launch of 24 leaves, ACCPRCP is the sum of PRCP x dt in step
+    order, and the six sums close the water balance of the column with the storage change (func:688-721 per step)."""
+    w = synth.make_workload("global025", ncol=200, nsteps=24)
+    f = synth.forcing_all(w)
+    kw = dict(dt=w.dt, zsoil=synth.ZSOIL, yearlen=w.yearlen, zref=w.zref, co2_frac=w.co2_frac, o2_frac=w.o2_frac, foln=w.foln)
+    s1, d1 = w.state.copy(), np.zeros((L.NDIAG, w.ncol), f32)
+    orc.run(s1, f, w.static_f, w.static_i, julian0=w.julian0, diag=d1, **kw)
+    s2, d2 = w.state.copy(), np.zeros((L.NDIAG, w.ncol), f32)
+    orc.run(s2, np.ascontiguousarray(f[:12]), w.static_f, w.static_i, julian0=w.julian0, diag=d2, **kw)
+    orc.run(s2, np.ascontiguousarray(f[12:]), w.static_f, w.static_i, julian0=w.julian0 + 12 * w.dt / 86400.0, diag=d2, **kw)
+    assert np.array_equal(s1.view(np.int32), s2.view(np.int32)) and np.array_equal(d1.view(np.int32), d2.view(np.int32))
+    acc = np.zeros(w.ncol, f32)
+    for s in range(24):
+        acc = acc + f[s, L.F["PRCP"]] * f32(w.dt)
+    assert np.array_equal(d1[L.D["ACCPRCP"]], acc) and (acc > 0).any()
+    assert (d1[L.D["SFCRNOFF"]] >= 0).all() and np.isfinite(d1[L.ACC_DIAG_PLANES[0]:]).all()
+    # water balance over the launch: storage change = P - E - R (mm), up to the per-step residuals
+    def storage(st):
+        tot = st[L.S["CANLIQ"]] + st[L.S["CANICE"]] + st[L.S["SNEQV"]] + st[L.S["WA"]]
+        dz = np.diff(np.concatenate([[0.0], -np.asarray(synth.ZSOIL)]))
+        return tot.astype(np.float64) + sum(st[L.smc(k)].astype(np.float64) * dz[k - 1] * 1000.0 for k in range(1, 5))
+    D = L.D
+    net = (d1[D["ACCPRCP"]].astype(np.float64) - d1[D["ACCECAN"]] - d1[D["ACCETRAN"]] - d1[D["ACCEDIR"]] - d1[D["SFCRNOFF"]]
+           - d1[D["UGDRNOFF"]])
+    assert np.abs(storage(s1) - storage(w.state) - net).max() < 0.05

@@ -485,3 +485,26 @@ def test_type_indices_outside_the_tables_are_flagged_not_fatal(tables):
     assert not gd[np.ix_(other, idx)].any()
     assert np.isfinite(gb).all()
     assert int(gb[L.B["NCELL"]]) == w.ncol - len(bad)
+
+
+def test_accumulated_diagnostics_on_the_gpu(tables, oracle_libs):
+    """ACCPRCP ... UGDRNOFF: read-modify-write planes.  Two launches of 12 steps into the same diag buffer == one launch of 24
+    == the strict oracle, bit for bit; `noahmp_run_host` starts them at zero whatever the host buffer held."""
+    w = synth.make_workload("global025", ncol=1000, nsteps=24)
+    f = synth.forcing_all(w)
+    cs, cd, _ = cpu_run(tables, w, f, "strict", diag=True)
+    eng = NoahMP(tables, w.opts, device=0, fast="strict")
+    st = torch.from_numpy(w.state.copy()).to(DEV)
+    dg = torch.zeros((L.NDIAG, w.ncol), dtype=torch.float32, device=DEV)
+    sf, si, fo = torch.from_numpy(w.static_f).to(DEV), torch.from_numpy(w.static_i).to(DEV), torch.from_numpy(f).to(DEV)
+    rp = lambda s0: eng.run_params(w.dt, synth.ZSOIL, w.julian0 + s0 * w.dt / 86400.0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)  # noqa: E731
+    eng.run(rp(0), st, fo[:12], sf, si, dg, None)
+    eng.run(rp(12), st, fo[12:], sf, si, dg, None)
+    torch.cuda.synchronize()
+    acc = slice(L.ACC_DIAG_PLANES[0], L.NDIAG)
+    assert np.array_equal(dg[acc].cpu().numpy().view(np.int32), cd[acc].view(np.int32))
+    assert np.array_equal(st.cpu().numpy()[:L.NSTATE_CORE].view(np.int32), cs[:L.NSTATE_CORE].view(np.int32))
+    hs, hd = w.state.copy(), np.full((L.NDIAG, w.ncol), 7.0, f32)
+    eng.run_host(rp(0), hs, f, w.static_f, w.static_i, hd)
+    assert np.array_equal(hd[acc].view(np.int32), cd[acc].view(np.int32))
+    eng.close()
