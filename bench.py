@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-sort-columns", action="store_true", help="keep the generator's random column order")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-variants", action="store_true", help="skip timing the parity/strict builds")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the other BASELINE configs (N = 1 default line)")
     ap.add_argument("--e2e-steps-per-launch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-cols", type=int, default=1_000_000)
@@ -105,37 +106,49 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-def ncu_traffic(nloc, nsteps, variant):
-    """DRAM bytes per launch of the step kernel from the committed ncu capture, if it is of this exact launch."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            t = json.load(fh)
-        if t["columns"] == nloc and t["model_steps"] == nsteps and t["variant"] == variant:
-            return t["traffic_bytes_per_launch"]
-    except Exception:
-        pass
+def _capture():
+    """The committed ncu capture of the step kernel on the benchmark workload: this round's if there is one."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                t = json.load(fh)
+            t["file"] = "profiles/" + name
+            return t
+        except Exception:
+            continue
     return None
+
+
+def ncu_traffic(nloc, nsteps, variant):
+    """(DRAM bytes per launch, where the figure comes from): read from the committed `ncu --set full` capture when it is of
+    this exact launch (same columns, fused steps and build) - it is a citation of that capture, not a live measurement."""
+    t = _capture()
+    if t and t["columns"] == nloc and t["model_steps"] == nsteps and t["variant"] == variant:
+        return t["traffic_bytes_per_launch"], f"{t['file']} ({t.get('capture', 'ncu --set full')}); not measured in this run"
+    return None, "no committed capture of this exact launch"
 
 
 def issue_roofline(cell_steps_per_s, variant, sm_count, sm_mhz):
     """The bound the kernel actually runs against: one warp-instruction per scheduler per clock (4 schedulers per SM).
     Warp-instructions per cell-step come from the committed ncu capture of this workload (profiles/r01_traffic.json)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            t = json.load(fh)
-        if t["variant"] != variant or not sm_mhz:
+        t = _capture()
+        if t is None or t["variant"] != variant or not sm_mhz:
             return None
         per = t["warp_inst"] / (t["columns"] * t["model_steps"])
         peak = sm_count * 4 * sm_mhz * 1e6
         return {"bound": "issue", "warp_inst_per_cell_step": per, "achieved": cell_steps_per_s * per, "peak": peak,
                 "unit": "warp-inst/s", "frac": cell_steps_per_s * per / peak,
-                "source": "instruction count of profiles/r01_traffic.json (ncu), SM clock sampled during the timed region"}
+                "source": f"instruction count of {t['file']} (ncu), SM clock sampled during the timed region"}
     except Exception:
         return None
 
 
 def build_workload(args):
+    """The workload of the generators, re-ordered by divergence class.  `w.order[j]` = generator id of the column at position
+    j: the forcing generator hashes that id, so every column keeps its own forcing whatever the order and the rank count."""
     w = synth.make_workload(args.workload, ncol=args.ncol, nsteps=args.model_steps)
+    w.order = np.arange(w.ncol, dtype=np.int64)
     if not args.no_sort_columns:
         # divergence-class ordering (SURVEY 8e), balanced over the ranks; done once at set-up
         world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -144,6 +157,7 @@ def build_workload(args):
         w.static_f = np.ascontiguousarray(w.static_f[:, order])
         w.static_i = np.ascontiguousarray(w.static_i[order])
         w.sincos = np.ascontiguousarray(w.sincos[:, order])
+        w.order = np.ascontiguousarray(order.astype(np.int64))
     return w
 
 
@@ -151,6 +165,7 @@ def slice_workload(w, c0, n):
     import copy
     s = copy.copy(w)
     s.ncol = n
+    s.order = np.ascontiguousarray(w.order[c0:c0 + n])
     s.state = np.ascontiguousarray(w.state[:, c0:c0 + n])
     s.static_f = np.ascontiguousarray(w.static_f[:, c0:c0 + n])
     s.static_i = np.ascontiguousarray(w.static_i[c0:c0 + n])
@@ -177,6 +192,7 @@ def sample_workload(w, n):
     s.static_f = np.ascontiguousarray(w.static_f[:, idx])
     s.static_i = np.ascontiguousarray(w.static_i[idx])
     s.sincos = np.ascontiguousarray(w.sincos[:, idx])
+    s.order = np.ascontiguousarray(w.order[idx])
     return s, idx
 
 
@@ -194,7 +210,7 @@ def cpu_baseline(w, sample_cols: int, fast: bool = True, repeats: int = 1) -> di
     from oracle.oracle import Oracle
     ws, idx = sample_workload(w, sample_cols)
     n = ws.ncol
-    forcing = synth.forcing_all(ws, cols=idx)
+    forcing = synth.forcing_all(ws, cols=ws.order)
     o = Oracle(ParamTables.default(), w.opts, fast="fast" if fast else "parity")
     best = None
     for _ in range(repeats):
@@ -217,7 +233,7 @@ def translated_reference_leg(w, sample_cols: int = 200_000):
         if not (os.path.exists(refrun.LIB) and os.path.exists(refrun.SIG)):
             return None
         ws, idx = sample_workload(w, sample_cols)
-        forcing = synth.forcing_all(ws, cols=idx)
+        forcing = synth.forcing_all(ws, cols=ws.order)
         ref = refrun.RefModel(ParamTables.default(), w.opts)
         st = ws.state.copy()
         t0 = time.perf_counter()
@@ -238,7 +254,7 @@ def run_reference(args):
     from oracle.oracle import Oracle
     ws, idx = sample_workload(w, args.cpu_sample_cols)
     n = ws.ncol
-    forcing = synth.forcing_all(ws, cols=idx)
+    forcing = synth.forcing_all(ws, cols=ws.order)
     o = Oracle(ParamTables.default(), w.opts, fast="fast")
     times = []
     for it in range(args.warmup + args.steps):
@@ -265,6 +281,149 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local: int) -> dict:
+    """Pin this rank to the CPUs next to its GPU (sysfs: the PCI device's local_cpulist / numa_node) BEFORE any pinned
+    buffer is allocated, so that the page-locked forcing records are first touched on the GPU's own NUMA node and the H2D
+    copies do not cross the socket interconnect.  No-op (and says so) where the topology is not exposed."""
+    import torch
+    info = {"applied": False}
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bus = f"{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        info.update({"pci": bus, "numa_node": node, "local_cpulist": cpulist})
+        cpus = set()
+        for part in cpulist.split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if node >= 0 and allowed and len(allowed) < len(os.sched_getaffinity(0)) and world > 1:
+            os.sched_setaffinity(0, allowed)
+            info["applied"] = True
+            info["cpus_bound"] = len(allowed)
+    except Exception as exc:  # topology not exposed (container, single node): leave the scheduler alone
+        info["note"] = f"{type(exc).__name__}: {exc}"
+    return info
+
+
+def h2d_probe(dev, world, nbytes=1 << 30, reps=6) -> dict:
+    """Host->device copy bandwidth of pinned memory with ALL ranks copying at once and no compute: the ceiling of any
+    end-to-end figure that streams forcing (a model step needs 32 B per column over this link)."""
+    import torch
+    import torch.distributed as dist
+    h = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    h.fill_(1.0)
+    d = torch.empty_like(h, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    gbs = nbytes * reps / float(el.item()) / 1e9
+    del h, d
+    return {"h2d_gbs_per_gpu": gbs, "h2d_gbs_all_gpus": gbs * world, "ranks_copying": world, "bytes_per_copy": nbytes, "copies": reps,
+            "e2e_ceiling_cell_steps_per_s": gbs * world * 1e9 / 32.0,
+            "note": "pinned host memory, all ranks at once, slowest rank's time; a model step streams 8 fp32 planes = 32 B per column"}
+
+
+def twin_sample(name, order, c0, nloc):
+    """Columns of the committed fp64-twin fixture (tests/golden/twin_<name>.npz) that this rank owns: (fixture, selector into the
+    fixture, local column positions).  `order` maps sorted position -> generator column id."""
+    path = os.path.join(ROOT, "tests", "golden", f"twin_{name}.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    ids = g["columns"]
+    if order is None:
+        pos = ids
+    else:
+        inv = np.empty(order.size, np.int64)
+        inv[order] = np.arange(order.size)
+        pos = inv[ids]
+    mine = (pos >= c0) & (pos < c0 + nloc)
+    return g, np.where(mine)[0], pos[mine] - c0
+
+
+def parity_of(state_planes, fixture, sel):
+    """Distance of the sampled columns from the fp64 twin of the reference, beside the fp32 reference's own (tools/accuracy.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import accuracy as A
+    cmp = A.compare(state_planes[:L.NSTATE_CORE], fixture["ref32"][:, sel], fixture["ref64"][:, sel])
+    out = A.summary(cmp)
+    out["source"] = "sampled columns of this run against tests/golden/twin_*.npz (translated reference, fp32 and fp64, full step count)"
+    return out
+
+
+def run_other_workload(name, nsteps, twin_name, variant, dev, stream, peak, sm_count, clocks_mhz):
+    """One more BASELINE config on this GPU, full size and full length: forcing generated on the device 24 steps at a time, the
+    step launches timed with CUDA events (forcing generation outside the events), sampled columns set against the fp64 twin."""
+    import torch
+    from noahmp_b200.engine import NoahMP
+    w = synth.make_workload(name, nsteps=nsteps)
+    order = divergence_order(w.static_i, w.static_f[L.C["LAT"]], 1) if w.ncol > 1 else np.zeros(1, np.int64)
+    state = np.ascontiguousarray(w.state[:, order])
+    eng = NoahMP(ParamTables.default(), w.opts, device=dev.index, fast=variant)
+    eng.set_stream(stream)
+    with torch.cuda.stream(stream):
+        st = torch.from_numpy(state).to(dev)
+        sf = torch.from_numpy(np.ascontiguousarray(w.static_f[:, order])).to(dev)
+        si = torch.from_numpy(np.ascontiguousarray(w.static_i[order])).to(dev)
+        sincos = torch.from_numpy(np.ascontiguousarray(w.sincos[:, order])).to(dev)
+        ids = torch.from_numpy(order.astype(np.int64)).to(dev)
+        chunk = 24
+        fo = torch.empty((chunk, L.NFORCING, w.ncol), dtype=torch.float32, device=dev)
+        bd = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
+    coef = synth.synth_params_array(w.synth)
+    evs = []
+    l0 = eng.launch_count()
+    # the generator hashes each column's GENERATOR id (ids), so the re-ordered columns keep their own forcing
+    with torch.cuda.stream(stream):
+        for s0 in range(0, w.nsteps, chunk):
+            n = min(chunk, w.nsteps - s0)
+            for s in range(n):
+                sc = synth.step_scalars(w, s0 + s)
+                eng.synth_forcing_ids(ids, w.synth.seed, s0 + s, coef,
+                                      np.asarray([sc["sd"], sc["cdch"], sc["t_diur"], sc["t_seas"]], np.float32), sincos, fo[s])
+            rp = eng.run_params(w.dt, synth.ZSOIL, w.julian0 + s0 * w.dt / 86400.0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            eng.run(rp, st, fo[:n], sf, si, None, bd)
+            e1.record(stream)
+            evs.append((e0, e1))
+    stream.synchronize()
+    kern_s = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+    cs = w.ncol * w.nsteps
+    b = bd.cpu().numpy()
+    out = {"workload": name, "columns": w.ncol, "model_steps": w.nsteps, "dt_s": w.dt, "cell_steps": cs, "variant": variant,
+           "value": cs / kern_s, "unit": UNIT, "kernel_s": kern_s, "launches": int(eng.launch_count() - l0 - w.nsteps),
+           "roofline_frac": B_ALG * cs / kern_s / 1e9 / peak, "flagged_column_launches": int(b[L.B["NFLAGGED"]]),
+           "max_abs_water_error_mm": float(b[L.B["ERRWAT_MAXABS"]]), "sneqv_mean_mm": float(b[L.B["SNEQV"]] / max(b[L.B["NCELL"]], 1.0)),
+           "timing": "CUDA events around the step launches only (forcing generation is outside)"}
+    iss = issue_roofline(cs / kern_s, variant, sm_count, clocks_mhz)
+    if iss:
+        out["issue_frac_at_conus_instruction_count"] = iss["frac"]
+    if twin_name:
+        ts = twin_sample(twin_name, order, 0, w.ncol)
+        if ts is not None and w.nsteps == int(ts[0]["nsteps"]) and w.ncol == int(ts[0]["ncol"]):
+            g, sel, pos = ts
+            out["parity"] = parity_of(st[:, torch.from_numpy(pos).to(dev)].cpu().numpy(), g, sel)
+    eng.close()
+    del st, sf, si, fo
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -277,10 +436,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA GPU (no CPU fallback exists)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
     w = build_workload(args)
+    order = w.order
     c0, nloc = shard(w.ncol, rank, world)
     ws = slice_workload(w, c0, nloc)
     eng = NoahMP(ParamTables.default(), w.opts, device=local, fast=args.variant)
@@ -289,19 +450,21 @@ def run_ours(args):
     rp_of = lambda j0: eng.run_params(w.dt, synth.ZSOIL, j0, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln)  # noqa: E731
 
     # ---- inputs resident in HBM: state, static, forcing of every model step (generated on device) -----
-    launches0 = eng.launch_count()
     with torch.cuda.stream(stream):
         state0 = torch.from_numpy(ws.state).to(dev)
         state = state0.clone()
         static_f = torch.from_numpy(ws.static_f).to(dev)
         static_i = torch.from_numpy(ws.static_i).to(dev)
         sincos = torch.from_numpy(ws.sincos).to(dev)
+        ids = torch.from_numpy(ws.order).to(dev)
         forcing = torch.empty((w.nsteps, L.NFORCING, nloc), dtype=torch.float32, device=dev)
         coef = synth.synth_params_array(w.synth)
+        scal = []
         for s in range(w.nsteps):
             sc = synth.step_scalars(w, s)
-            eng.synth_forcing(nloc, c0, w.synth.seed, s, coef,
-                              np.asarray([sc["sd"], sc["cdch"], sc["t_diur"], sc["t_seas"]], np.float32), sincos, forcing[s])
+            scal.append(sc)
+            eng.synth_forcing_ids(ids, w.synth.seed, s, coef,
+                                  np.asarray([sc["sd"], sc["cdch"], sc["t_diur"], sc["t_seas"]], np.float32), sincos, forcing[s])
         budget = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
     stream.synchronize()
 
@@ -336,32 +499,34 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     total_ms_max = float(t_max.item())
+    peak, peak_src = measured_peak_gbs()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
     # ---- auxiliary kernel of the widened path: forcing preparation, pure HBM streaming
     aux = {}
     try:
         from noahmp_b200 import forcing as FRC
-        geo = torch.from_numpy(FRC.geo_planes(ws.static_f[L.C["LAT"]], np.zeros(nloc))).to(dev)
+        geo_p = torch.from_numpy(FRC.geo_planes(ws.static_f[L.C["LAT"]], np.zeros(nloc))).to(dev)
         out_f = torch.empty((L.NFORCING, nloc), dtype=torch.float32, device=dev)
         r0 = forcing[0, :8].contiguous()
         r1 = forcing[min(1, w.nsteps - 1), :8].contiguous()
         sc = FRC.solar_scalars(__import__("datetime").datetime(2000, 7, 1, 18))
         with torch.cuda.stream(stream):
             for _ in range(3):
-                eng.prepare_forcing(r0, r1, 0.25, geo, sc, out_f)
+                eng.prepare_forcing(r0, r1, 0.25, geo_p, sc, out_f)
             p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             p0.record(stream)
             for _ in range(10):
-                eng.prepare_forcing(r0, r1, 0.25, geo, sc, out_f)
+                eng.prepare_forcing(r0, r1, 0.25, geo_p, sc, out_f)
             p1.record(stream)
         stream.synchronize()
         pms = p0.elapsed_time(p1) / 10.0
         pbytes = 4 * nloc * (16 + 4 + 9)
-        peak_p, _src = measured_peak_gbs()
         aux["prepare_forcing"] = {"ms": pms, "bytes_per_launch": pbytes, "achieved_gbs": pbytes / (pms * 1e-3) / 1e9,
-                                  "frac_of_measured_hbm": pbytes / (pms * 1e-3) / 1e9 / peak_p, "bound": "hbm",
-                                  "note": "29 words per column, 128-bit accesses; buffers (2 GB at 17e6 columns) exceed L2"}
-        del geo, out_f, r0, r1
+                                  "frac_of_measured_hbm": pbytes / (pms * 1e-3) / 1e9 / peak, "bound": "hbm",
+                                  "note": "29 words per column, 128-bit accesses; buffers (2 GB at 17e6 columns) exceed L2; the "
+                                          "records-driven launches of `e2e` do this arithmetic inside the step kernel instead"}
+        del geo_p, out_f, r0, r1
     except Exception as exc:  # pragma: no cover - diagnostics only
         aux["prepare_forcing"] = {"error": str(exc)}
 
@@ -392,50 +557,80 @@ def run_ours(args):
             eng_v.close()
             del st_v
 
-    # ---- budget diagnostics of one extra pass + the only collective of the path (outside the timed region)
+    # ---- one extra pass from the initial state with the budget sums: domain diagnostics, and the state every parity figure
+    # of this line is computed on (24 model steps from the generator's initial columns)
     with torch.cuda.stream(stream):
         chk = state0.clone()
         eng.run(rp_of(w.julian0), chk, forcing, static_f, static_i, None, budget)
     stream.synchronize()
     bud = budget_means(allreduce_budget(budget.clone()).cpu().numpy(), w.nsteps)
+    parity = None
+    try:
+        if w.name == "conus1km" and args.ncol is None and args.model_steps is None:
+            ts = twin_sample("conus1km_day", order, c0, nloc)
+            if ts is not None and len(ts[1]):
+                g, sel, pos = ts
+                parity = parity_of(chk[:, torch.from_numpy(pos).to(dev)].cpu().numpy(), g, sel)
+                parity["rank0_columns_of_sample"] = int(len(sel))
+    except Exception as exc:  # pragma: no cover - the line must survive a missing fixture
+        parity = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- e2e through the host-facing C-ABI entry points -------------------------------------------------
-    # (1) headline `e2e`: noahmp_advance_host -- the time-marching pattern: column state and static planes
-    #     resident on the device (uploaded once, like weights), every model step's forcing copied from PINNED host
-    #     memory inside the timed region (double-buffered, overlapped with compute), the step's result (16 fp64
-    #     budget sums) read back to the host every bench step.
+    # (1) headline `e2e`: noahmp_advance_records_host -- the time-marching pattern: column state, static and position planes
+    #     resident on the device (uploaded once), every model step's forcing RECORD (8 fp32 planes) copied from PINNED host
+    #     memory inside the timed region (ring of device slots, copies overlapped with compute), time interpolation and COSZ
+    #     done in the step kernel's load, the 16 fp64 budget sums read back and all-reduced over the ranks every bench step.
     # (2) `e2e_state_roundtrip`: noahmp_run_host -- additionally moves the whole state H2D and D2H every step.
     e2e = None
     e2e_rt = None
+    probe = None
     if not args.no_e2e:
+        probe = h2d_probe(dev, world)
         nplanes = L.NSTATE_CORE if w.opts == synth.DEFAULT_OPTS else L.NSTATE
-        h_forcing = torch.empty((w.nsteps, L.NFORCING, nloc), dtype=torch.float32).pin_memory()
-        h_forcing.copy_(forcing)
+        h_records = torch.empty((w.nsteps, 8, nloc), dtype=torch.float32).pin_memory()
+        h_records.copy_(forcing[:, :8])
         h_budget = torch.zeros(L.NBUDGET, dtype=torch.float64).pin_memory()
+        # position planes of the synthetic grid: sin(lat), cos(lat) as the generator has them, longitude 0; the generator's COSZ
+        # = sin(lat) sd + cos(lat) (cos(decl) cos(H)) is the kernel's formula with cd = 1, ch0 = cos(decl) cos(H), sh0 = 0
+        geo = torch.stack([sincos[0], sincos[1], torch.zeros_like(sincos[0]), torch.ones_like(sincos[0])]).contiguous()
+        steps_tab = eng.step_table(list(range(w.nsteps)), list(range(w.nsteps)), [0.0] * w.nsteps,
+                                   [(sc["sd"], 1.0, sc["cdch"], 0.0) for sc in scal])
         torch.cuda.synchronize()
         ne2e = max(1, min(args.steps, 3))
         st_e = state0.clone()
-        eng.advance_host(rp_of(w.julian0), st_e, h_forcing, static_f, static_i, h_budget, args.e2e_steps_per_launch)  # warm-up
+        spl = args.e2e_steps_per_launch
+        eng.advance_records_host(rp_of(w.julian0), st_e, h_records, steps_tab, geo, static_f, static_i, h_budget, spl)  # warm-up
+        same = bool(torch.equal(st_e[:nplanes].view(torch.int32), chk[:nplanes].view(torch.int32)))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         l_e = eng.launch_count()
         t0 = time.perf_counter()
         flagged = 0
+        gsum = None
         for k in range(ne2e):
-            flagged += eng.advance_host(rp_of(w.julian0 + (k + 1) * w.nsteps * w.dt / 86400.0), st_e, h_forcing, static_f,
-                                        static_i, h_budget, args.e2e_steps_per_launch)
+            flagged += eng.advance_records_host(rp_of(w.julian0 + (k + 1) * w.nsteps * w.dt / 86400.0), st_e, h_records, steps_tab, geo,
+                                                static_f, static_i, h_budget, spl)
+            # the path's only collective, at diagnostics cadence (one model day), inside the timed region
+            gsum = allreduce_budget(h_budget.to(dev, non_blocking=True))
+        if gsum is not None:
+            gsum = gsum.cpu()
         dt_e = time.perf_counter() - t0
         t_e = torch.tensor([dt_e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": w.ncol * w.nsteps * ne2e / float(t_e.item()), "unit": UNIT,
-               "h2d_bytes_per_step": 4 * w.ncol * w.nsteps * L.NFORCING, "d2h_bytes_per_step": 8 * L.NBUDGET * world,
-               "steps": ne2e, "api": "noahmp_advance_host", "steps_per_launch": args.e2e_steps_per_launch,
+               "h2d_bytes_per_step": 4 * w.ncol * w.nsteps * 8, "d2h_bytes_per_step": 8 * L.NBUDGET * world,
+               "steps": ne2e, "api": "noahmp_advance_records_host", "steps_per_launch": spl,
                "gpu_launches": int(eng.launch_count() - l_e), "flagged": int(flagged),
-               "note": "state resident on device; forcing streamed from pinned host memory, budget read back"}
+               "state_equals_resident_path": same, "collective": "budget all-reduce (15 x SUM + 1 x MAX, fp64) once per bench step, timed",
+               "host_link": probe, "cpu_binding": numa,
+               "note": "state resident on device; forcing RECORDS (8 planes) streamed from pinned host memory, each once; time "
+                       "interpolation + COSZ in the step kernel's load; budget read back and all-reduced"}
         del st_e
         # (2) full state round trip
+        h_forcing = torch.empty((w.nsteps, L.NFORCING, nloc), dtype=torch.float32).pin_memory()
+        h_forcing.copy_(forcing)
         h_state = torch.from_numpy(ws.state.copy()).pin_memory()
         h_sf = torch.from_numpy(ws.static_f).pin_memory()
         h_si = torch.from_numpy(ws.static_i).pin_memory()
@@ -452,13 +647,51 @@ def run_ours(args):
         e2e_rt = {"value": w.ncol * w.nsteps * ne2e / float(t_r.item()), "unit": UNIT,
                   "h2d_bytes_per_step": 4 * w.ncol * (nplanes + w.nsteps * L.NFORCING + L.NSTATIC_F + 1),
                   "d2h_bytes_per_step": 4 * w.ncol * nplanes, "steps": ne2e, "api": "noahmp_run_host"}
-        del h_state, h_forcing
+        del h_state, h_forcing, h_records
+
+    # ---- the other BASELINE configs at full size and length on this GPU (N = 1 only: they fit one GPU many times over)
+    others = None
+    if world == 1 and not args.no_other_workloads and w.name == "conus1km" and args.ncol is None:
+        del forcing, state, chk, state0
+        torch.cuda.empty_cache()
+        others = {}
+        mhz = (clocks or {}).get("sm_mhz")
+        for name, nsteps, twin in (("snow1m", 720, "snow1m_month"), ("global025", 8760, "global025_year"),
+                                   ("uniform100k", 48, "uniform100k"), ("single", 96, None)):
+            try:
+                others[name] = run_other_workload(name, nsteps, twin, args.variant, dev, stream, peak, sm_count, mhz)
+            except Exception as exc:  # pragma: no cover
+                others[name] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:   # the run-time-options kernel once (all 12 options as kernel arguments, 57-plane state): opt_tbot = 2 costs the same physics
+            wopt = synth.make_workload("conus1km", ncol=2_000_000, nsteps=24, opts=[1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 2, 1])
+            o2 = divergence_order(wopt.static_i, wopt.static_f[L.C["LAT"]], 1)
+            eng_o = NoahMP(ParamTables.default(), wopt.opts, device=local, fast=args.variant)
+            eng_o.set_stream(stream)
+            with torch.cuda.stream(stream):
+                st_o = torch.from_numpy(np.ascontiguousarray(wopt.state[:, o2])).to(dev)
+                sf_o = torch.from_numpy(np.ascontiguousarray(wopt.static_f[:, o2])).to(dev)
+                si_o = torch.from_numpy(np.ascontiguousarray(wopt.static_i[o2])).to(dev)
+                fo_o = torch.from_numpy(np.ascontiguousarray(synth.forcing_all(wopt)[:, :, o2])).to(dev)
+                rp_o = eng_o.run_params(wopt.dt, synth.ZSOIL, wopt.julian0, wopt.yearlen, wopt.zref, wopt.co2_frac, wopt.o2_frac, wopt.foln)
+                eng_o.run(rp_o, st_o, fo_o, sf_o, si_o)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(3):
+                    eng_o.run(rp_o, st_o, fo_o, sf_o, si_o)
+                e1.record(stream)
+            stream.synchronize()
+            others["runtime_options_kernel"] = {"workload": "conus1km", "columns": wopt.ncol, "model_steps": 24, "options": wopt.opts,
+                                                "value": wopt.ncol * 24 * 3 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
+                                                "kernel": eng_o.kernel_info(), "note": "OptRuntime instantiation, 57-plane state"}
+            eng_o.close()
+        except Exception as exc:  # pragma: no cover
+            others["runtime_options_kernel"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         value = w.ncol * w.nsteps * args.steps / (total_ms_max * 1e-3)
-        peak, peak_src = measured_peak_gbs()
         k_ms = float(np.mean(per_launch_ms))
         achieved = B_ALG * nloc * w.nsteps / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(nloc, w.nsteps, args.variant)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
@@ -468,15 +701,15 @@ def run_ours(args):
                           if nloc * 4 * (2 * 44 + 9 * w.nsteps) > 2 * 126e6 else "inputs fit L2: traffic is L2-resident",
                     "kernel": eng.kernel_info()}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": ncu_traffic(nloc, w.nsteps, args.variant), "traffic_unit": "bytes per launch (ncu dram__bytes_read+write)",
+                             "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write)",
+                             "traffic_source": traffic_src,
                              "algorithmic_bytes_per_launch": B_ALG * nloc * w.nsteps, "peak_source": peak_src, "bytes_per_cell_step": B_ALG,
                              "kernel": "column_step_kernel", "kernel_ms": k_ms,
                              "note": "kernel is instruction-issue bound (see profiles/); fraction is reported against HBM as "
                                      "the contract asks"},
-                "e2e": e2e, "e2e_state_roundtrip": e2e_rt, "other_variants": other, "aux_kernels": aux, "gpu_launches": int(launches), "clocks": clocks, "budget": bud}
-        line["roofline_issue"] = issue_roofline(nloc * w.nsteps / (k_ms * 1e-3), args.variant,
-                                                torch.cuda.get_device_properties(dev).multi_processor_count,
-                                                (clocks or {}).get("sm_mhz"))
+                "e2e": e2e, "e2e_state_roundtrip": e2e_rt, "parity": parity, "other_variants": other, "other_workloads": others,
+                "aux_kernels": aux, "gpu_launches": int(launches), "clocks": clocks, "budget": bud}
+        line["roofline_issue"] = issue_roofline(nloc * w.nsteps / (k_ms * 1e-3), args.variant, sm_count, (clocks or {}).get("sm_mhz"))
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_sample_cols)
             tr = translated_reference_leg(w)

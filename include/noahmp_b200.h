@@ -117,6 +117,37 @@ int64_t noahmp_advance_host(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_
                             float* state_dev, const float* forcing_host, const float* static_f_dev,
                             const int32_t* static_i_dev, double* budget_host, int steps_per_launch);
 
+/* ---- records-driven launches: forcing ingest fused into the step kernel -------------------
+ * The namelist gives forcing records at `input_frequency` and a model step of `interval_seconds`
+ * (offline/noahmp_config.py:81-82,98).  Instead of preparing nine forcing planes per step in a pass of its own
+ * (noahmp_prepare_forcing below) the step kernel can read the RECORDS: per step it interpolates the two bracketing
+ * records and computes COSZ from the column's position - the same round-to-nearest arithmetic, bit for bit - so a
+ * record crosses PCIe / HBM once however many model steps it serves, and 8 planes travel instead of 9. */
+#define NOAHMP_MAX_RECORD_STEPS 32   /* model steps of one records-driven kernel launch */
+typedef struct noahmp_step_forcing {
+  int   rec0, rec1;        /* the two bracketing records: forcing = rec0 + weight * (rec1 - rec0), plane by plane     */
+  float weight;            /* (t - t0) / (t1 - t0) in [0,1]; 0: rec1 is not read                                      */
+  float sd, cd, ch0, sh0;  /* sin / cos of the solar declination, cos / sin of the hour angle at longitude 0          */
+} noahmp_step_forcing;
+
+/* noahmp_run with the forcing given as records: record r at records_dev + r*record_stride, each [8][ncol] (SFCTMP SFCPRS UU
+ * VV Q2 SOLDN LWDN PRCP); steps[nsteps] is a HOST array; geo_dev [4][ncol] = sin(lat) cos(lat) sin(lon) cos(lon).
+ * nsteps beyond NOAHMP_MAX_RECORD_STEPS is cut into several launches.  Otherwise as noahmp_run. */
+int noahmp_run_records(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+                       const float* records_dev, int64_t record_stride, const noahmp_step_forcing* steps,
+                       const float* geo_dev, const float* static_f_dev, const int32_t* static_i_dev, float* diag_dev,
+                       double* budget_dev);
+
+/* Streaming variant (the time-marching driver's call): state, static and geo planes stay on the device, the records
+ * arrive from the host.  records_host is [nrec][8][ncol] (page-locked for the copies to overlap); steps[nsteps] index
+ * into it.  Every record is copied H2D ONCE, on a private copy stream into a ring of device slots, while earlier
+ * launches compute (`steps_per_launch` model steps per launch, 1..NOAHMP_MAX_RECORD_STEPS).  Returns like
+ * noahmp_advance_host. */
+int64_t noahmp_advance_records_host(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t ncol, int nsteps,
+                                    float* state_dev, const float* records_host, int nrec,
+                                    const noahmp_step_forcing* steps, const float* geo_dev, const float* static_f_dev,
+                                    const int32_t* static_i_dev, double* budget_host, int steps_per_launch);
+
 /* ---- synthetic forcing generator (benchmark support; no counterpart in the reference) ------------
  * Fills forcing_dev [NFORCING][ncol] for one step with the hash-based generator of
  * noahmp_b200/synth.py (bit-identical).  sincos_dev [2][ncol] = sin(lat), cos(lat).
@@ -124,6 +155,11 @@ int64_t noahmp_advance_host(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_
 int noahmp_synth_forcing(noahmp_ctx* ctx, int64_t ncol, int64_t col0, uint32_t seed, int step,
                          const float* coef17, const float* step_scalars4, const float* sincos_dev,
                          float* forcing_dev);
+
+/* the same for re-ordered columns: ids_dev [ncol] int64 = each column's id in the generator's numbering */
+int noahmp_synth_forcing_ids(noahmp_ctx* ctx, int64_t ncol, const int64_t* ids_dev, uint32_t seed, int step,
+                             const float* coef17, const float* step_scalars4, const float* sincos_dev,
+                             float* forcing_dev);
 
 /* ---- forcing preparation (the caller side of the path; the reference has the namelist
  * fields `input_frequency` / `interval_seconds` but no code): time-interpolate two forcing records to the model

@@ -13,9 +13,15 @@ class RunParams(C.Structure):  # struct noahmp_run_params
                 ("co2_frac", C.c_float), ("o2_frac", C.c_float), ("foln", C.c_float), ("yearlen", C.c_int)]
 
 
+class StepForcing(C.Structure):  # struct noahmp_step_forcing
+    _fields_ = [("rec0", C.c_int), ("rec1", C.c_int), ("weight", C.c_float), ("sd", C.c_float), ("cd", C.c_float),
+                ("ch0", C.c_float), ("sh0", C.c_float)]
+
+
 # every symbol declared in include/noahmp_b200.h
 SYMBOLS = ["noahmp_init", "noahmp_finalize", "noahmp_set_stream", "noahmp_last_error", "noahmp_set_options",
-           "noahmp_set_tables", "noahmp_run", "noahmp_run_host", "noahmp_advance_host", "noahmp_synth_forcing", "noahmp_prepare_forcing", "noahmp_layout",
+           "noahmp_set_tables", "noahmp_run", "noahmp_run_host", "noahmp_advance_host", "noahmp_run_records",
+           "noahmp_advance_records_host", "noahmp_synth_forcing", "noahmp_synth_forcing_ids", "noahmp_prepare_forcing", "noahmp_layout",
            "noahmp_state_plane_name", "noahmp_forcing_plane_name", "noahmp_diag_plane_name", "noahmp_budget_name",
            "noahmp_launch_count", "noahmp_kernel_info"]
 
@@ -53,7 +59,12 @@ def load(fast=False) -> C.CDLL:
     lib.noahmp_run_host.restype = C.c_int64
     lib.noahmp_advance_host.argtypes = [vp, C.POINTER(RunParams), C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     lib.noahmp_advance_host.restype = C.c_int64
+    sfp = C.POINTER(StepForcing)
+    lib.noahmp_run_records.argtypes = [vp, C.POINTER(RunParams), C.c_int64, C.c_int, vp, vp, C.c_int64, sfp, vp, vp, vp, vp, vp]
+    lib.noahmp_advance_records_host.argtypes = [vp, C.POINTER(RunParams), C.c_int64, C.c_int, vp, vp, C.c_int, sfp, vp, vp, vp, vp, C.c_int]
+    lib.noahmp_advance_records_host.restype = C.c_int64
     lib.noahmp_synth_forcing.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, C.c_int, fp, fp, vp, vp]
+    lib.noahmp_synth_forcing_ids.argtypes = [vp, C.c_int64, vp, C.c_uint32, C.c_int, fp, fp, vp, vp]
     lib.noahmp_prepare_forcing.argtypes = [vp, C.c_int64, vp, vp, C.c_float, vp, fp, vp]
     lib.noahmp_layout.argtypes = [C.c_int]
     for f in ("noahmp_state_plane_name", "noahmp_forcing_plane_name", "noahmp_diag_plane_name", "noahmp_budget_name"):

@@ -6,13 +6,28 @@
 // steps of the launch (time fusion: only the 9 forcing planes are read per step) and stored once.
 #pragma once
 #include "water.cuh"
+#include "forcing_prep.cuh"
 
 namespace nmp {
 
+// One model step of a records-driven launch (include/noahmp_b200.h: noahmp_step_forcing): the forcing of the step is
+// the time interpolation of two records and COSZ follows from the column's position - the arithmetic of
+// forcing_prep.cuh, done in the load of the step kernel instead of in a pass of its own.
+struct StepForcing {
+  int rec0, rec1;           // the two bracketing records (slots of the record buffer)
+  float w;                  // weight of rec1 (0: rec1 is not read)
+  float sd, cd, ch0, sh0;   // solar scalars of the step
+};
+constexpr int MAX_RECORD_STEPS = 32;   // steps of one records-driven launch (the table travels as kernel parameters)
+
 struct StepArgs {
   float* state;           // [NSTATE][ncol]
-  const float* forcing;   // step s at forcing + s*forcing_stride, [NFORCING][ncol]
+  const float* forcing;   // step s at forcing + s*forcing_stride, [NFORCING][ncol]; null in records mode
   int64_t forcing_stride;
+  const float* records;   // records mode: record r at records + r*record_stride, [8][ncol]
+  int64_t record_stride;
+  const float* geo;       // records mode: [4][ncol] sin(lat) cos(lat) sin(lon) cos(lon)
+  StepForcing tab[MAX_RECORD_STEPS];
   const float* static_f;  // [NSTATIC_F][ncol]
   const int* static_i;    // [ncol]
   float* diag;            // [NDIAG][ncol] or null
@@ -123,7 +138,33 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
 #pragma unroll 1
   for (int s = 0; s < a.nsteps; ++s) {
     Forcing f;
-    {
+    if (a.records != nullptr) {   // records mode (uniform branch): interpolate + COSZ here, bit-identical to forcing_prep.cuh
+      const StepForcing sf = a.tab[s];
+      const float* R = a.records + (int64_t)sf.rec0 * a.record_stride + ii;
+      float v[8];
+      if (sf.w == 0.0f) {
+        static_for<0, 7>([&](auto q_) { constexpr int q = decltype(q_)::value; v[q] = ld_forcing(R + q * n); });
+      } else {
+        const float* R1 = a.records + (int64_t)sf.rec1 * a.record_stride + ii;
+        static_for<0, 7>([&](auto q_) { constexpr int q = decltype(q_)::value;
+          v[q] = lerp_rn(ld_forcing(R + q * n), ld_forcing(R1 + q * n), sf.w);
+        });
+      }
+      f.SFCTMP = v[F_SFCTMP]; f.SFCPRS = v[F_SFCPRS]; f.UU = v[F_UU]; f.VV = v[F_VV]; f.Q2 = v[F_Q2]; f.SOLDN = v[F_SOLDN];
+      f.LWDN = v[F_LWDN]; f.PRCP = v[F_PRCP];
+      PrepScalars ps;
+      ps.w = sf.w; ps.sd = sf.sd; ps.cd = sf.cd; ps.ch0 = sf.ch0; ps.sh0 = sf.sh0;
+      const float* G = a.geo + ii;
+      f.COSZ = cosz_rn(ld_forcing(G), ld_forcing(G + n), ld_forcing(G + 2 * n), ld_forcing(G + 3 * n), ps);
+#ifdef NMP_PREFETCH_FORCING
+      if (s + 1 < a.nsteps) {
+        const float* Rn = a.records + (int64_t)a.tab[s + 1].rec0 * a.record_stride + ii;
+        static_for<0, 7>([&](auto q_) { constexpr int q = decltype(q_)::value;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Rn + q * n));
+        });
+      }
+#endif
+    } else {
       const float* F = a.forcing + (int64_t)s * a.forcing_stride + ii;
       f.SFCTMP = ld_forcing(F + F_SFCTMP * n); f.SFCPRS = ld_forcing(F + F_SFCPRS * n); f.UU = ld_forcing(F + F_UU * n);
       f.VV = ld_forcing(F + F_VV * n); f.Q2 = ld_forcing(F + F_Q2 * n); f.SOLDN = ld_forcing(F + F_SOLDN * n);

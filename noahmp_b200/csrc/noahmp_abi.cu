@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/noahmp_b200.h"
 #include "column_step.cuh"
@@ -38,6 +39,12 @@ struct noahmp_ctx {
   float* fbuf[2] = {nullptr, nullptr};
   size_t cap_fbuf = 0;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  // noahmp_advance_records_host: ring of record slots on the device, one last-use event per slot
+  float* rring = nullptr;
+  size_t cap_rring = 0;            // bytes
+  int rring_slots = 0;
+  cudaEvent_t* ev_slot = nullptr;  // [rring_slots]
+  cudaEvent_t ev_rcopied = nullptr;
   int64_t launches = 0;
   std::string err;
 };
@@ -112,12 +119,13 @@ struct SynthCoef {
 #define ADD(a, b) __fadd_rn((a), (b))
 #define SUB(a, b) __fsub_rn((a), (b))
 #define MUL(a, b) __fmul_rn((a), (b))
-__global__ void __launch_bounds__(256) synth_forcing_kernel(int64_t ncol, int64_t col0, SynthCoef p,
+__global__ void __launch_bounds__(256) synth_forcing_kernel(int64_t ncol, int64_t col0, const int64_t* __restrict__ ids, SynthCoef p,
                                                             const float* __restrict__ sincos,
                                                             float* __restrict__ forcing) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncol) return;
-  const uint32_t col = (uint32_t)(uint64_t)(col0 + i);
+  // the generator hashes the column's id in the GENERATOR's numbering: col0 + i, or ids[i] when the columns were re-ordered
+  const uint32_t col = (uint32_t)(uint64_t)(ids ? ids[i] : col0 + i);
   float u[12];
 #pragma unroll
   for (int s = 0; s < 12; ++s) {
@@ -199,6 +207,10 @@ int noahmp_finalize(noahmp_ctx* c) {
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  cudaFree(c->rring);
+  for (int k = 0; k < c->rring_slots; ++k) cudaEventDestroy(c->ev_slot[k]);
+  delete[] c->ev_slot;
+  if (c->ev_rcopied) cudaEventDestroy(c->ev_rcopied);
   delete c;
   return 0;
 }
@@ -249,23 +261,44 @@ int noahmp_set_tables(noahmp_ctx* c, const float* gen, int ngen, const float* so
   return 0;
 }
 
+// where the forcing of a launch comes from: prepared planes [nsteps][9][ncol], or records + per-step table + geo planes
+struct ForcingSource {
+  const float* forcing = nullptr; int64_t forcing_stride = 0;
+  const float* records = nullptr; int64_t record_stride = 0; const float* geo = nullptr; const noahmp_step_forcing* steps = nullptr;
+};
+
 static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
-                    const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,
+                    const ForcingSource& src, const float* static_f_dev,
                     const int32_t* static_i_dev, float* diag_dev, double* budget_dev, int final_launch) {
   if (!c) return -1;
   if (!c->have_opts) return fail(c, -4, "noahmp_set_options has not been called");
   if (!c->have_tables) return fail(c, -4, "noahmp_set_tables has not been called");
   if (ncol < 0 || nsteps < 0) return fail(c, -1, "negative size");
   if (ncol == 0 || nsteps == 0) return 0;   // empty batch: nothing to do (an empty tensor has a null pointer)
-  if (!rp || !state_dev || !forcing_dev || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
+  if (!rp || !state_dev || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
+  if (!src.forcing && !(src.records && src.geo && src.steps)) return fail(c, -1, "null argument");
+  if (src.records) {
+    if (nsteps > MAX_RECORD_STEPS) return fail(c, -1, "records-driven launch longer than NOAHMP_MAX_RECORD_STEPS");
+    for (int s = 0; s < nsteps; ++s) {
+      if (src.steps[s].rec0 < 0 || src.steps[s].rec1 < 0) return fail(c, -5, "negative record index");
+      if (!(src.steps[s].weight >= 0.0f && src.steps[s].weight <= 1.0f)) return fail(c, -5, "interpolation weight must be in [0,1]");
+    }
+  }
   if (!(rp->dt > 0.0f) || rp->yearlen <= 0) return fail(c, -5, "dt and yearlen must be positive");
   if (!std::isfinite(rp->julian0)) return fail(c, -5, "julian0 must be finite (it is wrapped into [0, yearlen) per step)");
   for (int k = 0; k < 4; ++k)
     if (!(rp->zsoil[k] < (k ? rp->zsoil[k - 1] : 0.0f))) return fail(c, -5, "zsoil must be negative and decreasing");
   CUDA_TRY(c, cudaSetDevice(c->device));
   StepArgs a;
-  a.state = state_dev; a.forcing = forcing_dev; a.forcing_stride = forcing_step_stride; a.static_f = static_f_dev;
+  a.state = state_dev; a.forcing = src.forcing; a.forcing_stride = src.forcing_stride; a.static_f = static_f_dev;
   a.static_i = static_i_dev; a.diag = diag_dev;
+  a.records = src.records; a.record_stride = src.record_stride; a.geo = src.geo;
+  std::memset(a.tab, 0, sizeof(a.tab));
+  if (src.records)
+    for (int s = 0; s < nsteps; ++s) {
+      const noahmp_step_forcing& q = src.steps[s];
+      a.tab[s] = StepForcing{q.rec0, q.rec1, q.weight, q.sd, q.cd, q.ch0, q.sh0};
+    }
   a.budget = budget_dev ? budget_dev : c->dev_budget_scratch;
   a.tables = c->dev_tables; a.ncol = ncol; a.nsteps = nsteps; a.final_launch = final_launch;
   a.rc.dt = rp->dt;
@@ -286,8 +319,38 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
 int noahmp_run(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
                const float* forcing_dev, int64_t forcing_step_stride, const float* static_f_dev,
                const int32_t* static_i_dev, float* diag_dev, double* budget_dev) {
-  return run_impl(c, rp, ncol, nsteps, state_dev, forcing_dev, forcing_step_stride, static_f_dev, static_i_dev, diag_dev,
-                  budget_dev, 1);
+  ForcingSource src;
+  src.forcing = forcing_dev; src.forcing_stride = forcing_step_stride;
+  if (!forcing_dev && ncol > 0 && nsteps > 0) return fail(c, -1, "null argument");
+  return run_impl(c, rp, ncol, nsteps, state_dev, src, static_f_dev, static_i_dev, diag_dev, budget_dev, 1);
+}
+
+static int run_records_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+                            const float* records_dev, int64_t record_stride, const noahmp_step_forcing* steps,
+                            const float* geo_dev, const float* static_f_dev, const int32_t* static_i_dev, float* diag_dev,
+                            double* budget_dev, int final_launch) {
+  if (!c) return -1;
+  if (ncol < 0 || nsteps < 0) return fail(c, -1, "negative size");
+  if (ncol == 0 || nsteps == 0) return 0;
+  if (!rp || !records_dev || !steps || !geo_dev) return fail(c, -1, "null argument");
+  for (int s0 = 0; s0 < nsteps; s0 += MAX_RECORD_STEPS) {   // the step table travels as kernel parameters: 32 steps a launch
+    const int n = nsteps - s0 < MAX_RECORD_STEPS ? nsteps - s0 : MAX_RECORD_STEPS;
+    noahmp_run_params r = *rp;
+    r.julian0 = rp->julian0 + (double)s0 * (double)rp->dt / 86400.0;
+    ForcingSource src;
+    src.records = records_dev; src.record_stride = record_stride; src.geo = geo_dev; src.steps = steps + s0;
+    const int rc = run_impl(c, &r, ncol, n, state_dev, src, static_f_dev, static_i_dev, diag_dev, budget_dev,
+                            (final_launch && s0 + n >= nsteps) ? 1 : 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int noahmp_run_records(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+                       const float* records_dev, int64_t record_stride, const noahmp_step_forcing* steps, const float* geo_dev,
+                       const float* static_f_dev, const int32_t* static_i_dev, float* diag_dev, double* budget_dev) {
+  return run_records_impl(c, rp, ncol, nsteps, state_dev, records_dev, record_stride, steps, geo_dev, static_f_dev, static_i_dev,
+                          diag_dev, budget_dev, 1);
 }
 
 int64_t noahmp_run_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state,
@@ -370,7 +433,9 @@ int64_t noahmp_advance_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t 
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_copied[b], 0));
     noahmp_run_params r = *rp;
     r.julian0 = rp->julian0 + (double)s0 * (double)rp->dt / 86400.0;
-    const int rc = run_impl(c, &r, ncol, n, state_dev, c->fbuf[b], (int64_t)step_words, static_f_dev, static_i_dev, nullptr,
+    ForcingSource src;
+    src.forcing = c->fbuf[b]; src.forcing_stride = (int64_t)step_words;
+    const int rc = run_impl(c, &r, ncol, n, state_dev, src, static_f_dev, static_i_dev, nullptr,
                             c->dev_budget_scratch, s0 + g >= nsteps ? 1 : 0);
     if (rc) return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev_done[b], cs));
@@ -382,8 +447,109 @@ int64_t noahmp_advance_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t 
   return (int64_t)llround(bsum[B_NFLAGGED]);
 }
 
-int noahmp_synth_forcing(noahmp_ctx* c, int64_t ncol, int64_t col0, uint32_t seed, int step, const float* coef17,
-                         const float* sc4, const float* sincos_dev, float* forcing_dev) {
+int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
+                                    const float* records_host, int nrec, const noahmp_step_forcing* steps,
+                                    const float* geo_dev, const float* static_f_dev, const int32_t* static_i_dev,
+                                    double* budget_host, int steps_per_launch) {
+  if (!c) return -1;
+  if (ncol <= 0 || nsteps <= 0) return 0;
+  if (!rp || !state_dev || !records_host || !steps || !geo_dev || !static_f_dev || !static_i_dev) return fail(c, -1, "null argument");
+  for (int s = 0; s < nsteps; ++s) {
+    const noahmp_step_forcing& q = steps[s];
+    if (q.rec0 < 0 || q.rec0 >= nrec || q.rec1 < 0 || q.rec1 >= nrec) return fail(c, -5, "record index outside records_host");
+    if (!(q.weight >= 0.0f && q.weight <= 1.0f)) return fail(c, -5, "interpolation weight must be in [0,1]");
+  }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int g = steps_per_launch > 0 ? steps_per_launch : 1;
+  if (g > nsteps) g = nsteps;
+  if (g > MAX_RECORD_STEPS) g = MAX_RECORD_STEPS;
+  // records a launch can touch: at most two per step; the ring holds two launches' worth so that the copies of launch
+  // k+1 run while launch k computes (a record shared by consecutive launches is copied once)
+  const int slots = 4 * g < 4 ? 4 : 4 * g;
+  const size_t rec_words = (size_t)8 * (size_t)ncol;
+  if (!c->copy_stream) {
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    }
+  }
+  if (!c->ev_rcopied) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_rcopied, cudaEventDisableTiming));
+  if (slots > c->rring_slots) {
+    cudaEvent_t* ev = new cudaEvent_t[slots];
+    for (int k = 0; k < slots; ++k) {
+      if (k < c->rring_slots) ev[k] = c->ev_slot[k];
+      else CUDA_TRY(c, cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    }
+    delete[] c->ev_slot;
+    c->ev_slot = ev;
+    c->rring_slots = slots;
+  }
+  const size_t need = sizeof(float) * rec_words * (size_t)c->rring_slots;
+  if (need > c->cap_rring) {
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->rring) cudaFree(c->rring);
+    c->rring = nullptr;
+    c->cap_rring = 0;
+    CUDA_TRY(c, cudaMalloc((void**)&c->rring, need));
+    c->cap_rring = need;
+  }
+  const int R = c->rring_slots;
+  cudaStream_t cs = c->stream;
+  CUDA_TRY(c, cudaMemsetAsync(c->dev_budget_scratch, 0, sizeof(double) * NBUDGET, cs));
+  // nothing of an earlier call may still read the ring when the first copy lands
+  for (int k = 0; k < R; ++k) CUDA_TRY(c, cudaEventRecord(c->ev_slot[k], cs));
+  std::vector<int> resident((size_t)R, -1);
+  noahmp_step_forcing tab[MAX_RECORD_STEPS];
+  for (int s0 = 0; s0 < nsteps; s0 += g) {
+    const int n = (nsteps - s0 < g) ? nsteps - s0 : g;
+    bool copied = false;
+    std::vector<int> claimed((size_t)R, -1);   // record each slot holds for THIS launch
+    for (int s = 0; s < n; ++s) {
+      const noahmp_step_forcing& q = steps[s0 + s];
+      const int need_rec[2] = {q.rec0, q.weight == 0.0f ? q.rec0 : q.rec1};
+      for (int k = 0; k < 2; ++k) {
+        const int r = need_rec[k], slot = r % R;
+        if (claimed[(size_t)slot] >= 0 && claimed[(size_t)slot] != r)
+          return fail(c, -5, "the records of one launch must be within 4 x steps_per_launch consecutive records");
+        claimed[(size_t)slot] = r;
+        if (resident[(size_t)slot] == r) continue;
+        CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_slot[slot], 0));   // last launch that read this slot
+        CUDA_TRY(c, cudaMemcpyAsync(c->rring + (size_t)slot * rec_words, records_host + (size_t)r * rec_words,
+                                    sizeof(float) * rec_words, cudaMemcpyHostToDevice, c->copy_stream));
+        resident[(size_t)slot] = r;
+        copied = true;
+      }
+      tab[s] = q;
+      tab[s].rec0 = need_rec[0] % R;
+      tab[s].rec1 = need_rec[1] % R;
+    }
+    if (copied) {
+      CUDA_TRY(c, cudaEventRecord(c->ev_rcopied, c->copy_stream));
+      CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_rcopied, 0));
+    }
+    noahmp_run_params r = *rp;
+    r.julian0 = rp->julian0 + (double)s0 * (double)rp->dt / 86400.0;
+    ForcingSource src;
+    src.records = c->rring; src.record_stride = (int64_t)rec_words; src.geo = geo_dev; src.steps = tab;
+    const int rc = run_impl(c, &r, ncol, n, state_dev, src, static_f_dev, static_i_dev, nullptr, c->dev_budget_scratch,
+                            s0 + g >= nsteps ? 1 : 0);
+    if (rc) return rc;
+    for (int s = 0; s < n; ++s) {   // the slots this launch reads are busy until it ends
+      CUDA_TRY(c, cudaEventRecord(c->ev_slot[tab[s].rec0], cs));
+      if (tab[s].rec1 != tab[s].rec0) CUDA_TRY(c, cudaEventRecord(c->ev_slot[tab[s].rec1], cs));
+    }
+  }
+  double bsum[NBUDGET];
+  CUDA_TRY(c, cudaMemcpyAsync(bsum, c->dev_budget_scratch, sizeof(double) * NBUDGET, cudaMemcpyDeviceToHost, cs));
+  CUDA_TRY(c, cudaStreamSynchronize(cs));
+  if (budget_host) std::memcpy(budget_host, bsum, sizeof(bsum));
+  return (int64_t)llround(bsum[B_NFLAGGED]);
+}
+
+static int synth_impl(noahmp_ctx* c, int64_t ncol, int64_t col0, const int64_t* ids_dev, uint32_t seed, int step, const float* coef17,
+                      const float* sc4, const float* sincos_dev, float* forcing_dev) {
   if (!c || !coef17 || !sc4 || !sincos_dev || !forcing_dev) return -1;
   if (ncol <= 0) return 0;
   CUDA_TRY(c, cudaSetDevice(c->device));
@@ -393,10 +559,21 @@ int noahmp_synth_forcing(noahmp_ctx* c, int64_t ncol, int64_t col0, uint32_t see
   p.seed = seed; p.step = step;
   const int block = 256;
   const int64_t grid = (ncol + block - 1) / block;
-  synth_forcing_kernel<<<(unsigned)grid, block, 0, c->stream>>>(ncol, col0, p, sincos_dev, forcing_dev);
+  synth_forcing_kernel<<<(unsigned)grid, block, 0, c->stream>>>(ncol, col0, ids_dev, p, sincos_dev, forcing_dev);
   c->launches += 1;
   CUDA_TRY(c, cudaGetLastError());
   return 0;
+}
+
+int noahmp_synth_forcing(noahmp_ctx* c, int64_t ncol, int64_t col0, uint32_t seed, int step, const float* coef17,
+                         const float* sc4, const float* sincos_dev, float* forcing_dev) {
+  return synth_impl(c, ncol, col0, nullptr, seed, step, coef17, sc4, sincos_dev, forcing_dev);
+}
+
+int noahmp_synth_forcing_ids(noahmp_ctx* c, int64_t ncol, const int64_t* ids_dev, uint32_t seed, int step, const float* coef17,
+                             const float* sc4, const float* sincos_dev, float* forcing_dev) {
+  if (!ids_dev) return -1;
+  return synth_impl(c, ncol, 0, ids_dev, seed, step, coef17, sc4, sincos_dev, forcing_dev);
 }
 
 int noahmp_prepare_forcing(noahmp_ctx* c, int64_t ncol, const float* rec0_dev, const float* rec1_dev, float weight,

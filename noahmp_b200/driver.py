@@ -277,25 +277,45 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
     diag = torch.zeros((L.NDIAG, ncol), dtype=torch.float32, device=dev)
     budget = torch.zeros(L.NBUDGET, dtype=torch.float64, device=dev)
     end_slots = torch.tensor([L.B["NCELL"], L.B["SNEQV"], L.B["SOILWATER"]], device=dev)
-    forcing = torch.empty((max_steps_per_launch, L.NFORCING, ncol), dtype=torch.float32, device=dev)
+    # records-driven launches (noahmp_run_records): the forcing records go to the device once each and the step kernel
+    # interpolates them and computes COSZ in its own load - no prepared forcing planes, no preparation pass
+    max_steps_per_launch = min(max_steps_per_launch, 32)
     reader = F.RecordReader(cfg.indir, cfg.infreq, cfg.begdatetime, ntot, dev)
-    rec = (lambda when: reader.record(when)[:, mine].contiguous()) if world > 1 else reader.record
+    ring = F.RecordRing(reader, max_steps_per_launch + 2, mine, dev)
     nsteps, written = step0, []
+    timing = {"ingest_s": 0.0, "launch_s": 0.0, "gather_s": 0.0, "write_s": 0.0}
+    import time as _time
+    # wall-time split (ingest = record files -> device ring; kernel = step launches; gather = all-gather + D2H at output /
+    # restart cadence; write = files).  NOAHMP_TIMING=1 synchronises after every launch so that `kernel_s` is the device
+    # time and not the enqueue time; without it the launches overlap the next ingest and only the total is meaningful.
+    detail = os.environ.get("NOAHMP_TIMING", "0") == "1"
+    t_wall0 = _time.perf_counter()
     while t < cfg.enddatetime:
-        t_launch, g = t, 0
-        while g < max_steps_per_launch and t < cfg.enddatetime:
+        t_launch, plan = t, []
+        while len(plan) < max_steps_per_launch and t < cfg.enddatetime:
             t0, t1, wgt = reader.bracket(t)
-            eng.prepare_forcing(rec(t0), rec(t1), wgt, geo, F.solar_scalars(t), forcing[g])
-            g += 1
+            plan.append((t0, t1, wgt, F.solar_scalars(t)))
             t = t + dtm
             if F.is_boundary(t, cfg.begdatetime, out_freq) or F.is_boundary(t, cfg.begdatetime, res_freq):
                 break
+        g = len(plan)
+        tic = _time.perf_counter()
+        slot = ring.slots_for([p[0] for p in plan] + [p[1] for p in plan])
+        timing["ingest_s"] += _time.perf_counter() - tic
+        steps = eng.step_table([slot[p[0]] for p in plan], [slot[p[1]] for p in plan], [p[2] for p in plan], [p[3] for p in plan])
         rp = eng.run_params(dtm.total_seconds(), synth.ZSOIL, F.julian_of(t_launch), F.yearlen_of(t_launch))
         budget[end_slots] = 0.0   # NCELL / SNEQV / SOILWATER are end-of-launch snapshots: keep the last launch's only
-        eng.run(rp, state, forcing[:g], sf, si, diag, budget)
+        tic = _time.perf_counter()
+        eng.run_records(rp, state, ring.ring, steps, geo, sf, si, diag, budget)
+        if detail:
+            torch.cuda.synchronize()
+        timing["launch_s"] += _time.perf_counter() - tic
         nsteps += g
         if F.is_boundary(t, cfg.begdatetime, out_freq):
+            tic = _time.perf_counter()
             full = gather_columns(diag, ntot).cpu().numpy()
+            timing["gather_s"] += _time.perf_counter() - tic
+            tic = _time.perf_counter()
             if as_nc:
                 p = os.path.join(cfg.outdir, F.stamp(t) + ".LDASOUT_DOMAIN1")
             else:
@@ -307,9 +327,13 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
                 else:
                     np.savez(p, diag=full, planes=np.asarray(L.DIAG), time=F.stamp(t))
             written.append(p)
+            timing["write_s"] += _time.perf_counter() - tic
             diag[L.ACC_DIAG_PLANES[0]:] = 0.0   # ACCPRCP ... UGDRNOFF accumulate from one output to the next
         if F.is_boundary(t, cfg.begdatetime, res_freq):
+            tic = _time.perf_counter()
             full = gather_columns(state, ntot).cpu().numpy()
+            timing["gather_s"] += _time.perf_counter() - tic
+            tic = _time.perf_counter()
             if as_nc:
                 p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + "_DOMAIN1")
             else:
@@ -320,11 +344,16 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
                 else:
                     write_restart(p, full, t, nsteps)
             written.append(p)
+            timing["write_s"] += _time.perf_counter() - tic
     torch.cuda.synchronize()
+    timing["total_s"] = _time.perf_counter() - t_wall0
+    timing["synchronised_per_launch"] = detail
+    timing["records_loaded"] = ring.loads
     allreduce_budget(budget)
     out = _summary(gather_columns(state, ntot).cpu().numpy(), gather_columns(diag, ntot).cpu().numpy(), budget.cpu().numpy(), ntot,
                    nsteps, dtm.total_seconds(), cfg.physics_options())
     out["files_written"] = written
+    out["timing"] = timing
     out["launches"] = eng.launch_count()
     out["ranks"] = world
     eng.close()

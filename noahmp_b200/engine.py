@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import layout as L
-from ._lib import NoahMPLibraryError, RunParams, load
+from ._lib import NoahMPLibraryError, RunParams, StepForcing, load
 from .tables import ParamTables
 
 OPTION_ORDER = ["opt_veg", "opt_crs", "opt_btr", "opt_run", "opt_sfc", "opt_frz", "opt_inf", "opt_rad", "opt_alb",
@@ -126,9 +126,47 @@ class NoahMP:
                                                         _host_ptr(forcing_host), _dev_ptr(static_f), _dev_ptr(static_i),
                                                         _host_ptr(budget), int(steps_per_launch)), "noahmp_advance_host")
 
+    @staticmethod
+    def step_table(rec0, rec1, weight, scal4):
+        """``noahmp_step_forcing[nsteps]`` from per-step sequences: record indices, weights in [0,1] and the four solar
+        scalars (sin / cos of the declination, cos / sin of the hour angle at longitude 0; ``forcing.solar_scalars``)."""
+        n = len(rec0)
+        tab = (StepForcing * n)()
+        for s in range(n):
+            sc = scal4[s]
+            tab[s] = StepForcing(int(rec0[s]), int(rec1[s]), float(weight[s]), float(sc[0]), float(sc[1]), float(sc[2]), float(sc[3]))
+        return tab
+
+    def run_records(self, rp: RunParams, state, records, steps, geo, static_f, static_i, diag=None, budget=None) -> None:
+        """``noahmp_run_records``: like :meth:`run`, the forcing given as device records [nrec,8,ncol] + a step table
+        (:meth:`step_table`) + geo planes [4,ncol]; interpolation and COSZ happen in the step kernel's load."""
+        nrec, nv, ncol = records.shape
+        assert nv == 8 and state.shape == (L.NSTATE, ncol) and tuple(geo.shape) == (4, ncol)
+        assert all(0 <= s.rec0 < nrec and 0 <= s.rec1 < nrec for s in steps)
+        self._check(self.lib.noahmp_run_records(self.ctx, C.byref(rp), ncol, len(steps), _dev_ptr(state), _dev_ptr(records), 8 * ncol,
+                                                steps, _dev_ptr(geo), _dev_ptr(static_f), _dev_ptr(static_i), _dev_ptr(diag),
+                                                _dev_ptr(budget)), "noahmp_run_records")
+
+    def advance_records_host(self, rp: RunParams, state, records_host, steps, geo, static_f, static_i, budget=None,
+                             steps_per_launch: int = 1) -> int:
+        """``noahmp_advance_records_host``: device-resident state / static / geo planes, records [nrec,8,ncol] streamed from
+        (pinned) host memory, each copied once.  Returns the flagged column-launch count."""
+        nrec, nv, ncol = records_host.shape
+        assert nv == 8 and tuple(state.shape) == (L.NSTATE, ncol) and tuple(geo.shape) == (4, ncol)
+        return self._check(self.lib.noahmp_advance_records_host(self.ctx, C.byref(rp), ncol, len(steps), _dev_ptr(state),
+                                                                _host_ptr(records_host), nrec, steps, _dev_ptr(geo),
+                                                                _dev_ptr(static_f), _dev_ptr(static_i), _host_ptr(budget),
+                                                                int(steps_per_launch)), "noahmp_advance_records_host")
+
     def synth_forcing(self, ncol, col0, seed, step, coef17: np.ndarray, scalars4: np.ndarray, sincos, out) -> None:
         self._check(self.lib.noahmp_synth_forcing(self.ctx, ncol, col0, seed, step, _fp(coef17), _fp(scalars4),
                                                   _dev_ptr(sincos), _dev_ptr(out)), "noahmp_synth_forcing")
+
+    def synth_forcing_ids(self, ids, seed, step, coef17: np.ndarray, scalars4: np.ndarray, sincos, out) -> None:
+        """The generator for re-ordered columns: ``ids`` int64 device tensor [ncol] = generator column ids."""
+        assert ids.dtype.is_floating_point is False and ids.element_size() == 8
+        self._check(self.lib.noahmp_synth_forcing_ids(self.ctx, ids.shape[0], _dev_ptr(ids), seed, step, _fp(coef17), _fp(scalars4),
+                                                      _dev_ptr(sincos), _dev_ptr(out)), "noahmp_synth_forcing_ids")
 
     def prepare_forcing(self, rec0, rec1, weight: float, geo, scal4: np.ndarray, out) -> None:
         """``noahmp_prepare_forcing``: out[9,ncol] = time interpolation of two [8,ncol] records + COSZ (device tensors)."""

@@ -111,21 +111,58 @@ class RecordReader:
         t1 = t0 if w == 0.0 else t0 + dt.timedelta(seconds=n)
         return t0, t1, w
 
+    def load(self, t: dt.datetime) -> np.ndarray:
+        """The record of time ``t`` as a host array float32 [8][ncol] (no caching)."""
+        p = self.path(t)
+        if not os.path.isfile(p):
+            raise FileNotFoundError(f"ERR: Unable to find forcing record {p}")
+        if p.endswith(".npy"):
+            a = np.load(p)
+        else:
+            from . import ncio
+            a = ncio.read_record(p, self.ncol)
+        if a.shape != (len(RECORD_VARS), self.ncol) or a.dtype != np.float32:
+            raise ValueError(f"{p}: expected float32 [{len(RECORD_VARS)}][{self.ncol}], got {a.dtype} {a.shape}")
+        return a
+
     def record(self, t: dt.datetime):
         import torch
         key = stamp(t)
         if key not in self._cache:
-            p = self.path(t)
-            if not os.path.isfile(p):
-                raise FileNotFoundError(f"ERR: Unable to find forcing record {p}")
-            if p.endswith(".npy"):
-                a = np.load(p)
-            else:
-                from . import ncio
-                a = ncio.read_record(p, self.ncol)
-            if a.shape != (len(RECORD_VARS), self.ncol) or a.dtype != np.float32:
-                raise ValueError(f"{p}: expected float32 [{len(RECORD_VARS)}][{self.ncol}], got {a.dtype} {a.shape}")
+            a = self.load(t)
             if len(self._cache) >= 2:
                 self._cache.pop(sorted(self._cache)[0])
             self._cache[key] = torch.from_numpy(a).to(self.device)
         return self._cache[key]
+
+
+class RecordRing:
+    """Device ring of forcing records for records-driven launches (``noahmp_run_records``): a record is read from disk and
+    copied to the device once, however many model steps and launches it serves."""
+
+    def __init__(self, reader: RecordReader, slots: int, columns: slice, device):
+        import torch
+        self.reader, self.columns = reader, columns
+        n = columns.stop - columns.start
+        self.ring = torch.empty((slots, len(RECORD_VARS), n), dtype=torch.float32, device=device)
+        self.held: dict = {}      # stamp -> slot
+        self.loads = 0
+
+    def slots_for(self, times) -> dict:
+        """Make every record time in ``times`` resident; returns {time: slot}.  Slots of records this launch does not need
+        are recycled (stream order keeps earlier launches safe: copies and launches share the stream)."""
+        import torch
+        need = {stamp(t): t for t in times}
+        if len(need) > self.ring.shape[0]:
+            raise ValueError("a launch needs more records than the ring holds")
+        free = [s for s in range(self.ring.shape[0]) if s not in self.held.values()]
+        for key in [k for k in self.held if k not in need]:
+            free.append(self.held.pop(key))
+        for key, t in need.items():
+            if key not in self.held:
+                a = self.reader.load(t)[:, self.columns]
+                slot = free.pop()
+                self.ring[slot].copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=False)
+                self.held[key] = slot
+                self.loads += 1
+        return {t: self.held[stamp(t)] for t in times}

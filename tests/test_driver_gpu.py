@@ -186,3 +186,80 @@ def test_main_entry_point_runs_the_synthetic_single_point(tmp_path):
         os.chdir(cwd)
     assert s["steps"] == 96 and s["columns"] == 1 and s["flagged_column_launches"] == 0
     assert 250.0 < s["TG"] < 300.0 and s["max_abs_water_error_mm"] < 0.05
+
+
+# ---- records-driven launches: interpolation + COSZ fused into the step kernel's load --------------------------------------
+def _records_case(ncol, nrec=5, steps_per_record=4):
+    """nrec hourly records, steps_per_record model steps per record interval (the reference's own namelist: 900 s steps,
+    hourly input; run/case.nml:27, offline/noahmp_config.py:81-82)."""
+    w = synth.make_workload("global025", ncol=ncol, nsteps=1)
+    w.dt = 3600.0 / steps_per_record
+    rng = np.random.default_rng(11)
+    recs = np.stack([synth.forcing_step(w, h)[:8] for h in range(nrec)]).astype(np.float32)
+    lon = rng.uniform(-3.0, 3.0, ncol)
+    geo = F.geo_planes(w.static_f[L.C["LAT"]].astype(np.float64), lon)
+    t0 = dt.datetime(2000, 6, 30, 22)
+    plan = []
+    for s in range((nrec - 1) * steps_per_record):
+        t = t0 + dt.timedelta(seconds=s * w.dt)
+        r, k = divmod(s, steps_per_record)
+        plan.append((r, r + 1 if k else r, k / steps_per_record, F.solar_scalars(t)))
+    return w, recs, geo, plan, F.julian_of(t0), F.yearlen_of(t0)
+
+
+@pytest.mark.parametrize("variant", ["strict", "parity", "fast"])
+@pytest.mark.parametrize("ncol", [1, 777, 20_000])
+def test_records_launch_equals_prepared_forcing(tables, variant, ncol):
+    """noahmp_run_records == noahmp_prepare_forcing per step + noahmp_run, bit for bit (state, diagnostics, budget), in every
+    build: the fused load performs the preparation kernel's round-to-nearest arithmetic."""
+    w, recs, geo, plan, j0, ylen = _records_case(ncol)
+    eng = NoahMP(tables, w.opts, device=0, fast=variant)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    drecs, dgeo, sf, si = d(recs), d(geo), d(w.static_f), d(w.static_i)
+    n = len(plan)
+    forcing = torch.empty((n, L.NFORCING, ncol), dtype=torch.float32, device=DEV)
+    for s, (r0, r1, wt, sc) in enumerate(plan):
+        eng.prepare_forcing(drecs[r0], drecs[r1], wt, dgeo, sc, forcing[s])
+    rp = eng.run_params(w.dt, synth.ZSOIL, j0, ylen)
+    sa, da, ba = d(w.state), torch.zeros((L.NDIAG, ncol), dtype=torch.float32, device=DEV), torch.zeros(L.NBUDGET, dtype=torch.float64, device=DEV)
+    sb, db, bb = d(w.state), torch.zeros((L.NDIAG, ncol), dtype=torch.float32, device=DEV), torch.zeros(L.NBUDGET, dtype=torch.float64, device=DEV)
+    eng.run(rp, sa, forcing, sf, si, da, ba)
+    steps = eng.step_table([p[0] for p in plan], [p[1] for p in plan], [p[2] for p in plan], [p[3] for p in plan])
+    eng.run_records(rp, sb, drecs, steps, dgeo, sf, si, db, bb)
+    torch.cuda.synchronize()
+    assert torch.equal(sa.view(torch.int32), sb.view(torch.int32))
+    assert torch.equal(da.view(torch.int32), db.view(torch.int32))
+    assert torch.allclose(ba, bb, rtol=1e-12, atol=1e-9) and int(ba[L.B["NFLAGGED"]].item()) == 0   # fp64 atomics: addition order
+    # the same launch without diagnostics / budget (the benchmark's kernel variant)
+    sc_ = d(w.state)
+    eng.run_records(rp, sc_, drecs, steps, dgeo, sf, si)
+    torch.cuda.synchronize()
+    assert torch.equal(sa.view(torch.int32), sc_.view(torch.int32))
+    eng.close()
+
+
+@pytest.mark.parametrize("spl", [1, 3, 16])
+def test_streamed_records_equal_resident_records(tables, spl):
+    """noahmp_advance_records_host (records from pinned host memory through the device ring, each copied once) ==
+    noahmp_run_records on resident records; 40 steps exceed one launch's table (32), the ring wraps several times."""
+    w, recs, geo, plan, j0, ylen = _records_case(5000, nrec=11)
+    eng = NoahMP(tables, w.opts, device=0, fast="fast")
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    dgeo, sf, si = d(geo), d(w.static_f), d(w.static_i)
+    rp = eng.run_params(w.dt, synth.ZSOIL, j0, ylen)
+    steps = eng.step_table([p[0] for p in plan], [p[1] for p in plan], [p[2] for p in plan], [p[3] for p in plan])
+    sa, ba = d(w.state), torch.zeros(L.NBUDGET, dtype=torch.float64, device=DEV)
+    eng.run_records(rp, sa, d(recs), steps, dgeo, sf, si, None, ba)
+    sb = d(w.state)
+    hrec = torch.from_numpy(recs).pin_memory()
+    hb = torch.zeros(L.NBUDGET, dtype=torch.float64).pin_memory()
+    for _ in range(2):     # twice: the second call re-uses the ring of the first
+        sb.copy_(d(w.state))
+        nflag = eng.advance_records_host(rp, sb, hrec, steps, dgeo, sf, si, hb, spl)
+        assert nflag == 0
+        assert torch.equal(sa.view(torch.int32), sb.view(torch.int32))
+    bsum, ref = hb.numpy(), ba.cpu().numpy()
+    snap = [L.B["NCELL"], L.B["SNEQV"], L.B["SOILWATER"]]
+    assert np.array_equal(bsum[snap], ref[snap])
+    assert np.allclose(np.delete(bsum, snap), np.delete(ref, snap), rtol=1e-12, atol=1e-9)   # fp64 atomics: order of addition
+    eng.close()
