@@ -132,7 +132,9 @@ def read_var(path: str, name: str, tag: str = "", n: int = 1, kind=float):
         if len(vals) < n:
             raise ValueError
     except ValueError:
-        raise TableError(f"Unable to read {_nametag(name, tag)} from file {path}") from None
+        # the integer-scalar reader words it differently from the other three (utils:117 vs 141, 165, 189)
+        what = "Unable to read table" if (kind is int and n == 1) else "Unable to read"
+        raise TableError(f"{what} {_nametag(name, tag)} from file {path}") from None
     return vals[0] if n == 1 else vals
 
 

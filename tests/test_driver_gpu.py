@@ -230,11 +230,15 @@ def test_records_launch_equals_prepared_forcing(tables, variant, ncol):
     assert torch.equal(sa.view(torch.int32), sb.view(torch.int32))
     assert torch.equal(da.view(torch.int32), db.view(torch.int32))
     assert torch.allclose(ba, bb, rtol=1e-12, atol=1e-9) and int(ba[L.B["NFLAGGED"]].item()) == 0   # fp64 atomics: addition order
-    # the same launch without diagnostics / budget (the benchmark's kernel variant)
-    sc_ = d(w.state)
-    eng.run_records(rp, sc_, drecs, steps, dgeo, sf, si)
+    # the same pair without diagnostics / budget (the benchmark's kernel instantiation; in the fast build the instantiations are
+    # separately optimised code and need not agree with each other bit for bit, each agrees with itself across the two modes)
+    sc_, sd_ = d(w.state), d(w.state)
+    eng.run(rp, sc_, forcing, sf, si)
+    eng.run_records(rp, sd_, drecs, steps, dgeo, sf, si)
     torch.cuda.synchronize()
-    assert torch.equal(sa.view(torch.int32), sc_.view(torch.int32))
+    assert torch.equal(sc_.view(torch.int32), sd_.view(torch.int32))
+    if variant != "fast":
+        assert torch.equal(sa.view(torch.int32), sc_.view(torch.int32))
     eng.close()
 
 

@@ -95,3 +95,133 @@ def test_shipped_json_matches_reference_tbl(soil_tag, veg_tag):
     got = T.ParamTables.default(soil_tag, veg_tag).pack()
     for k in ref:
         assert np.array_equal(ref[k], got[k], equal_nan=True), k
+
+
+# ---- the readers inside the pin: the reference's readptable routines executed from their source text ---------------------
+COMBOS = [("STAS", "USGS"), ("STAS", "MODIFIED_IGBP_MODIS_NOAH"), ("STAS-RUC", "USGS"), ("STAS-RUC", "MODIFIED_IGBP_MODIS_NOAH")]
+
+
+def _module_arrays_of(t: T.ParamTables) -> dict:
+    """The product parser's values under the names of the reference's module variables (Fortran index order)."""
+    f32 = np.float32
+    out = {}
+    g = t.gen
+    for nm in ("CSOIL", "ZBOT", "CZIL", "DKREF", "KDTREF", "FRZK", "TIMEAN", "FSATMAX", "MLTFCT", "Z0SNO", "SSI", "SWEMAX", "BETADS",
+               "BETAIS", "EMSSOIL", "EMSLAKE"):
+        out["KK_" + nm] = f32(g[nm])
+    for nm in ("ALBICE", "ALBLAKE", "OMEGAS"):
+        out["KK_" + nm] = np.asarray(g[nm], f32)
+    out["LK_SLOPE"], out["NSLPTYP"] = np.asarray(g["SLOPE"], f32), len(g["SLOPE"])
+    for nm in T.SOIL_SLOTS:
+        out["LK_" + nm] = np.asarray(t.soil[nm], f32)
+    out["NSLTYP"], out["NSOILCOL"], out["NLUTYP"] = t.nsoiltyp, t.ncolor, t.nvegtyp
+    for nm in ("ALBSAT", "ALBDRY"):
+        out["LK_" + nm] = np.stack([np.asarray(t.color[nm + "_VIS"], f32), np.asarray(t.color[nm + "_NIR"], f32)])
+    v = t.veg_f
+    for nm in ("RHOL", "RHOS", "TAUL", "TAUS"):
+        out["LK_" + nm] = np.stack([np.asarray(v[nm + "_VIS"], f32), np.asarray(v[nm + "_NIR"], f32)])
+    for nm in ("LAI", "SAI"):
+        out[f"LK_{nm}12M"] = np.stack([np.asarray(v[f"{nm}{m:02d}"], f32) for m in range(1, 13)])
+    for nm in ["XL"] + T.VEG_PHYS + T.VEG_DVEG + T.VEG_PHOTO:
+        out["LK_" + nm] = np.asarray(v[nm], f32)
+    for nm in ("NROOT", "C3C4"):
+        out["LK_" + nm] = np.asarray(t.veg_i[nm], np.int32)
+    for nm in T.VEG_FLAGS:
+        out[nm] = int(t.flags[nm])
+    return out
+
+
+def _same_as_reference(ours: dict, ref: dict):
+    """Every array the product parser holds equals the reference routine's, on the rows the table has; beyond them the
+    reference's arrays keep their initial value (nan4 / 0)."""
+    for nm, a in ours.items():
+        r = np.asarray(ref[nm])
+        a = np.asarray(a)
+        if a.ndim == 0:
+            assert np.array_equal(a, r, equal_nan=True), nm
+            continue
+        head = r[..., :a.shape[-1]]
+        assert np.array_equal(a, head, equal_nan=True), nm
+        rest = r[..., a.shape[-1]:]
+        assert rest.size == 0 or (np.isnan(rest).all() if rest.dtype.kind == "f" else (rest == 0).all()), nm
+    # nothing the physics reads is missing from the product side (VOC and description tables feed only dead code)
+    unread = {k for k in ref if k.startswith(("LK_", "KK_")) and k not in ours} - {"LK_SLAREA", "LK_EPS"}
+    assert not unread, unread
+
+
+@pytest.mark.parametrize("soil_tag,veg_tag", COMBOS)
+def test_all_module_arrays_equal_the_committed_reader_output(soil_tag, veg_tag):
+    """tests/golden/tables_reference.npz (tools/make_table_fixture.py): what the reference's `*_readptable` routines,
+    executed from their Fortran text, leave in every LK_/KK_ array - against the shipped packed tables."""
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tables_reference.npz"))
+    ref = {k.split("|", 2)[2]: g[k] for k in g.files if k.startswith(f"{soil_tag}|{veg_tag}|")}
+    assert len(ref) >= 85
+    _same_as_reference(_module_arrays_of(T.ParamTables.default(soil_tag, veg_tag)), ref)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("soil_tag,veg_tag", COMBOS)
+def test_product_parser_equals_the_interpreted_reference_readers(soil_tag, veg_tag):
+    """Live: oracle/f90_tables.py runs gen -> soil -> veg readptable from /root/reference/core on /root/reference/tbl."""
+    from oracle import f90_tables
+    ref = f90_tables.read_all(os.path.join(REFERENCE, "tbl"), soil_tag, veg_tag)
+    _same_as_reference(_module_arrays_of(T.ParamTables.from_tbl_dir(os.path.join(REFERENCE, "tbl"), soil_tag, veg_tag)), ref)
+
+
+MALFORMED = {
+    # name: (file to damage, regex substitution, expected message fragment of the reference's assert)
+    "missing tag": ("SOILPARMMP.TBL", (r"&PARM#STAS\b(?!-)", "&PARM#OTHER"), "Unable to find PARM#STAS in file SOILPARMMP.TBL"),
+    "row count above the array": ("SOILPARMMP.TBL", (r"(&PARM#STAS\s*\n\s*)19", r"\g<1>31"), "Table PARM#STAS in file SOILPARMMP.TBL is too big to be read"),
+    "row count not a number": ("GENPARMMP.TBL", (r"(&SLOPE\s*\n\s*)9", r"\g<1>nine"), "Unable to read the number of rows for table SLOPE in file GENPARMMP.TBL"),
+    "table cut short": ("VEGPARMMP.TBL", (r"(?s)(&VOC#MODIFIED_IGBP_MODIS_NOAH.*?\n(?:.*\n){5}).*", r"\g<1>"), "Unable to read table VOC#MODIFIED_IGBP_MODIS_NOAH from file VEGPARMMP.TBL"),
+    "text where a number belongs": ("SOILPARMMP.TBL", (r"(&PARM#STAS\s*\n.*\n\s*1,\s*)2\.79", r"\g<1>abc"), "Unable to read PARM.STAS from file SOILPARMMP.TBL"),
+    "scalar missing": ("GENPARMMP.TBL", (r"&CZIL\b", "&CZIL_GONE"), "Unable to find CZIL in file GENPARMMP.TBL"),
+    "flag not an integer": ("VEGPARMMP.TBL", (r"(&ISURBAN#USGS\s*\n\s*)1", r"\g<1>1.5"), "Unable to read table ISURBAN#USGS from file VEGPARMMP.TBL"),
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("case", list(MALFORMED))
+def test_malformed_tables_raise_the_reference_messages(tmp_path, case):
+    """Both readers get the same damaged file; the product raises TableError where the reference's routine would
+    `assert` and `stop` (utils:43-53), with the reference's message."""
+    import re
+    import shutil
+    from oracle import f90_tables
+    fname, (pat, rep), msg = MALFORMED[case]
+    for f in (T.GEN_FILE, T.SOIL_FILE, T.VEG_FILE):
+        shutil.copy(os.path.join(REFERENCE, "tbl", f), tmp_path / f)
+    text = (tmp_path / fname).read_text()
+    damaged, n = re.subn(pat, rep, text, count=1)
+    assert n == 1, "the damage pattern must hit"
+    (tmp_path / fname).write_text(damaged)
+    veg_tag = "MODIFIED_IGBP_MODIS_NOAH" if "MODIS" in msg else "USGS"
+    with pytest.raises(f90_tables.FortranStop) as ref:
+        f90_tables.read_all(str(tmp_path), "STAS", veg_tag)
+    assert msg in str(ref.value)
+    if "VOC#" in msg:
+        return      # the product does not read the VOC table (it feeds only bvocflux, dead code at func:6749)
+    with pytest.raises(T.TableError) as got:
+        T.ParamTables.from_tbl_dir(str(tmp_path), "STAS", veg_tag)
+    ours = str(got.value).replace(str(tmp_path) + os.sep, "")
+    assert ours == str(ref.value), (ours, str(ref.value))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree only exists in the build container")
+def test_list_directed_forms_both_readers_accept(tmp_path):
+    """D exponents, quoted strings with commas, blanks instead of commas, a repeat count and trailing text."""
+    import shutil
+    from oracle import f90_tables
+    for f in (T.GEN_FILE, T.SOIL_FILE, T.VEG_FILE):
+        shutil.copy(os.path.join(REFERENCE, "tbl", f), tmp_path / f)
+    p = tmp_path / T.SOIL_FILE
+    text = p.read_text().splitlines()
+    i = next(k for k, ln in enumerate(text) if ln.strip().startswith("&PARM#STAS") and "RUC" not in ln)
+    row = text[i + 2]
+    vals = [v.strip() for v in row.split(",")]
+    text[i + 2] = f"{vals[0]}  {vals[1]} {vals[2]}, {vals[3]} ,{vals[4]}  0.069D0 4.66D-5 , 0.608E-6 {vals[8]} 'SAND, coarse' extra"
+    p.write_text("\n".join(text) + "\n")
+    ref = f90_tables.read_all(str(tmp_path), "STAS", "USGS")
+    _same_as_reference(_module_arrays_of(T.ParamTables.from_tbl_dir(str(tmp_path), "STAS", "USGS")), ref)
+    assert ref["LK_DKSAT"][0] == np.float32(4.66e-5) and ref["LK_PSISAT"][0] == np.float32(0.069)
