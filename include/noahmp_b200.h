@@ -183,6 +183,14 @@ const char* noahmp_budget_name(int i);
 int64_t noahmp_launch_count(const noahmp_ctx* ctx);
 /* registers / local-memory bytes / static smem of the step kernel variant that `noahmp_run` would use */
 int noahmp_kernel_info(noahmp_ctx* ctx, int info[4]);
+/* Debug instrumentation (no counterpart in the reference, which is compiled without bounds checks): in a library built
+ * with -DNMP_BOUNDS every data-dependent index of the step kernel is range-checked on the device (csrc/common.cuh,
+ * NMP_CHK); violations are counted and clamped, never made.  Returns 1 and the counts since the last reset (bit n of
+ * `sites` = site n was hit) in such a build, 0 (counts zero) in every other build, < 0 on error. */
+int noahmp_debug_bounds(noahmp_ctx* ctx, unsigned long long* hits, unsigned int* sites, int reset);
+/* launches one thread that selects element `idx` of a 4-element array through the checked helper (proves the checker
+ * counts); 1 in a -DNMP_BOUNDS build, 0 otherwise */
+int noahmp_debug_bounds_selftest(noahmp_ctx* ctx, int idx);
 
 #ifdef __cplusplus
 }

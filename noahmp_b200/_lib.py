@@ -23,7 +23,7 @@ SYMBOLS = ["noahmp_init", "noahmp_finalize", "noahmp_set_stream", "noahmp_last_e
            "noahmp_set_tables", "noahmp_run", "noahmp_run_host", "noahmp_advance_host", "noahmp_run_records",
            "noahmp_advance_records_host", "noahmp_synth_forcing", "noahmp_synth_forcing_ids", "noahmp_prepare_forcing", "noahmp_layout",
            "noahmp_state_plane_name", "noahmp_forcing_plane_name", "noahmp_diag_plane_name", "noahmp_budget_name",
-           "noahmp_launch_count", "noahmp_kernel_info"]
+           "noahmp_launch_count", "noahmp_kernel_info", "noahmp_debug_bounds", "noahmp_debug_bounds_selftest"]
 
 _cache: dict = {}
 
@@ -73,5 +73,7 @@ def load(fast=False) -> C.CDLL:
     lib.noahmp_launch_count.argtypes = [vp]
     lib.noahmp_launch_count.restype = C.c_int64
     lib.noahmp_kernel_info.argtypes = [vp, ip]
+    lib.noahmp_debug_bounds.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.c_int]
+    lib.noahmp_debug_bounds_selftest.argtypes = [vp, C.c_int]
     _cache[key] = lib
     return lib

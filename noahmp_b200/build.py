@@ -38,6 +38,8 @@ VARIANTS = {
     "parity": ("libnoahmp_b200.so", ["-fmad=false", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
     "fast": ("libnoahmp_b200_fast.so", ["--use_fast_math", "-DNMP_FAST_ALGEBRA", "-DNMP_BLOCK=256", "-DNMP_MIN_BLOCKS=3"]),
     "strict": ("libnoahmp_b200_strict.so", ["-fmad=false", "-DNMP_CR_LIBM", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
+    # the strict build with every data-dependent index range-checked on the device (common.cuh NMP_CHK): debug only
+    "bounds": ("libnoahmp_b200_bounds.so", ["-fmad=false", "-DNMP_CR_LIBM", "-DNMP_BOUNDS", "-DNMP_BLOCK=768", "-DNMP_MIN_BLOCKS=1"]),
 }
 
 

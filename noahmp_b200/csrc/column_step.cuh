@@ -118,9 +118,9 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
   const bool badtype = c.lutyp < 1 || c.lutyp > T.nvegtyp || c.sltyp < 1 || c.sltyp > T.nsoiltyp || c.ISC < 1 ||
                        c.ISC > T.ncolor || c.slptyp < 1 || c.slptyp > NGEN - G_SLOPE;
   if (badtype) { c.lutyp = 1; c.sltyp = 1; c.slptyp = 1; c.ISC = 1; }
-  const float* VG = &T.veg[(c.lutyp - 1) * NVEGF];
+  const float* VG = &T.veg[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGF];
   const int ISURBAN = T.flags[0], ISWATER = T.flags[1], ISBARREN = T.flags[2], ISICE = T.flags[3];
-  const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
+  const int NROOT = T.vegi[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGI + VI_NROOT];
 
   DiagSink<DIAG> dg;
   // only the owner of a column writes its diagnostics: tail threads shadow the last column and a column with a type
@@ -206,7 +206,7 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
     // ---- root-zone temperature and initial water storage, func:332-344 ---------------------------
     float TROOT = 0.0f;
     {
-      const float zroot = -pick(rc.zsoil, NROOT - 1);
+      const float zroot = root_depth(rc, NROOT);
       static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
         if (k <= NROOT) TROOT = TROOT + c.STC[IX7(k)] * DZSNSO[IX7(k)] / zroot;
       });
@@ -232,6 +232,8 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
         const float WT2 = 1.0f - WT1;
         if (IT1 < 1) IT1 = 12;
         if (IT2 > 12) IT2 = 1;
+        IT1 = NMP_CHK(IT1, 1, 12, 3);
+        IT2 = NMP_CHK(IT2, 1, 12, 3);
         LAI = WT1 * VG[V_LAI12M + IT1 - 1] + WT2 * VG[V_LAI12M + IT2 - 1];
         SAI = WT1 * VG[V_SAI12M + IT1 - 1] + WT2 * VG[V_SAI12M + IT2 - 1];
       }

@@ -223,12 +223,43 @@ __device__ __forceinline__ void static_for_rev(F&& f) {   // A, A-1, ..., B
   }
 }
 
+// ---- bounds-checked debug build (-DNMP_BOUNDS; compute-sanitizer is not available on the GPU pool) ------------------
+// Every data-dependent index of the step - pick(), the snow-pack scratch of combine / divide, the month indices of
+// phenology, the table rows - goes through NMP_CHK.  In the debug build an index outside [lo, hi] is counted, its site is
+// recorded (bit `site` of g_bounds_sites; read back with noahmp_debug_bounds) and the access is clamped instead of being
+// made; in every other build the macro is the index itself.  Sites: 0 pick() of a layer array, 1 combine's scratch,
+// 2 divide's scratch, 3 month index of phenology, 4 table row of a type index, 5 root-layer count, 6 water-table layer.
+#ifdef NMP_BOUNDS
+__device__ unsigned long long g_bounds_hits;
+__device__ unsigned int g_bounds_sites;
+__device__ __forceinline__ int bounds_chk(int idx, int lo, int hi, int site) {
+  if (idx < lo || idx > hi) {
+    atomicAdd(&g_bounds_hits, 1ull);
+    atomicOr(&g_bounds_sites, 1u << site);
+    return idx < lo ? lo : hi;
+  }
+  return idx;
+}
+#define NMP_CHK(idx, lo, hi, site) nmp::bounds_chk((idx), (lo), (hi), (site))
+#else
+#define NMP_CHK(idx, lo, hi, site) (idx)
+#endif
+
 // select element `idx` of a small register array without dynamic indexing
 template <int N>
-__device__ __forceinline__ float pick(const float (&a)[N], int idx) {
+__device__ __forceinline__ float pick(const float (&a)[N], int idx, int site = 0) {
+  idx = NMP_CHK(idx, 0, N - 1, site);
   float r = a[0];
   static_for<1, N - 1>([&](auto i_) { constexpr int i = decltype(i_)::value; r = (idx == i) ? a[i] : r; });
   return r;
+}
+
+// -ZSOIL(NROOT), the depth of the root zone (func:332-335, 1119-1140, 6700).  The reference evaluates it only inside loops
+// over layers 1..NROOT, so a type without roots (NROOT = 0: water, ice) never reads ZSOIL(0); here the value is formed
+// ahead of the (unrolled) loop and is unused in that case.  The debug build checks NROOT against 0..NSOIL.
+__device__ __forceinline__ float root_depth(const RunConst& rc, int NROOT) {
+  NROOT = NMP_CHK(NROOT, 0, NSOIL, 5);
+  return -pick(rc.zsoil, NROOT > 0 ? NROOT - 1 : 0);
 }
 
 }  // namespace nmp

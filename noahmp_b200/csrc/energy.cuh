@@ -732,8 +732,8 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
                                        const Forcing& f, float RHOAIR, float QAIR, float THAIR, float EAIR,
                                        float SWDOWN, float IGS, float HTOP, float elai, float esai, float fveg,
                                        const float (&DZSNSO_in)[7], EnergyResult& r, const DiagSink<DIAG>& dg) {
-  const float* VG = &T.veg[(c.lutyp - 1) * NVEGF];
-  const float* SP = &T.soil[(c.sltyp - 1) * NSOILP];
+  const float* VG = &T.veg[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGF];
+  const float* SP = &T.soil[NMP_CHK(c.sltyp - 1, 0, MAXSOILTYP - 1, 4) * NSOILP];
   const int ISURBAN = T.flags[0];
   const float DT = rc.dt;
   const int ISNOW = c.ISNOW;
@@ -845,7 +845,7 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
     static_for<0, (2) - 1>([&](auto ib_) { constexpr int ib = decltype(ib_)::value;
       float ALBSOD, ALBSOI;
       if (c.IST == 1) {
-        ALBSOD = fmin2(T.color[(c.ISC - 1) * NCOLORP + K_ALBSAT + ib] + INC, T.color[(c.ISC - 1) * NCOLORP + K_ALBDRY + ib]);
+        ALBSOD = fmin2(T.color[NMP_CHK(c.ISC - 1, 0, MAXCOLOR - 1, 4) * NCOLORP + K_ALBSAT + ib] + INC, T.color[NMP_CHK(c.ISC - 1, 0, MAXCOLOR - 1, 4) * NCOLORP + K_ALBDRY + ib]);
         ALBSOI = ALBSOD;
       } else if (c.TG > TFRZ) {
         ALBSOD = 0.06f / (m_powf(fmax2(0.01f, f.COSZ), 1.7f) + 0.15f);
@@ -930,13 +930,13 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
   else if (c.IST == 1) EMG = T.gen[G_EMSSOIL] * (1.0f - FSNO) + 1.0f * FSNO;
   else EMG = T.gen[G_EMSLAKE] * (1.0f - FSNO) + 1.0f * FSNO;
 
-  const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
+  const int NROOT = T.vegi[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGI + VI_NROOT];
   float BTRAN = 0.0f;
   static_for<0, (4) - 1>([&](auto k_) { constexpr int k = decltype(k_)::value;
     r.BTRANI[k] = 0.0f;
   });
   if (c.IST == 1) {                                                                       // func:1119-1140
-    const float zroot = -pick(rc.zsoil, NROOT - 1);
+    const float zroot = root_depth(rc, NROOT);
     static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
       if (k <= NROOT) {
         float GX = 0.0f;
@@ -1009,7 +1009,7 @@ __device__ __forceinline__ void energy(const Opt& opt, const Tables& T, const Ru
   LeafParams LP;
   LP.BP = VG[V_BP]; LP.MP = VG[V_MP]; LP.FOLNMX = VG[V_FOLNMX]; LP.QE25 = VG[V_QE25]; LP.KC25 = VG[V_KC25];
   LP.AKC = VG[V_AKC]; LP.KO25 = VG[V_KO25]; LP.AKO = VG[V_AKO]; LP.VCMX25 = VG[V_VCMX25]; LP.AVCMX = VG[V_AVCMX];
-  LP.C3C4 = T.vegi[(c.lutyp - 1) * NVEGI + VI_C3C4];
+  LP.C3C4 = T.vegi[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGI + VI_C3C4];
   Loop1 L;
   L.mo = mo; L.WSTAR = 0.0f; L.H = 0.0f; L.HG = 0.0f; L.FHG = 0.0f; L.TAH = TAH; L.EAH = EAH; L.TV = TV;
   L.LITER = 0; L.iter_done = 0; L.running = veg_tile ? 1 : 0;

@@ -631,4 +631,56 @@ int noahmp_kernel_info(noahmp_ctx* c, int info[4]) {
   return 0;
 }
 
+// ---- bounds-checked debug build (-DNMP_BOUNDS, common.cuh) -----------------------------------------------------------
+#ifdef NMP_BOUNDS
+namespace {
+__global__ void bounds_selftest_kernel(float* out, int idx) {
+  const float a[4] = {1.0f, 2.0f, 3.0f, 4.0f};
+  out[0] = nmp::pick(a, idx);   // idx outside 0..3: counted at site 0 and clamped
+}
+}  // namespace
+#endif
+
+int noahmp_debug_bounds(noahmp_ctx* c, unsigned long long* hits, unsigned int* sites, int reset) {
+  if (!c) return -1;
+  if (hits) *hits = 0;
+  if (sites) *sites = 0;
+#ifdef NMP_BOUNDS
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  unsigned long long h = 0;
+  unsigned int m = 0;
+  CUDA_TRY(c, cudaMemcpyFromSymbol(&h, nmp::g_bounds_hits, sizeof(h)));
+  CUDA_TRY(c, cudaMemcpyFromSymbol(&m, nmp::g_bounds_sites, sizeof(m)));
+  if (hits) *hits = h;
+  if (sites) *sites = m;
+  if (reset) {
+    h = 0; m = 0;
+    CUDA_TRY(c, cudaMemcpyToSymbol(nmp::g_bounds_hits, &h, sizeof(h)));
+    CUDA_TRY(c, cudaMemcpyToSymbol(nmp::g_bounds_sites, &m, sizeof(m)));
+  }
+  return 1;
+#else
+  (void)reset;
+  return 0;
+#endif
+}
+
+int noahmp_debug_bounds_selftest(noahmp_ctx* c, int idx) {
+  if (!c) return -1;
+#ifdef NMP_BOUNDS
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  float* d = nullptr;
+  CUDA_TRY(c, cudaMalloc(&d, sizeof(float)));
+  bounds_selftest_kernel<<<1, 1, 0, c->stream>>>(d, idx);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaFree(d));
+  return 1;
+#else
+  (void)idx;
+  return 0;
+#endif
+}
+
 }  // extern "C"

@@ -33,7 +33,7 @@ __device__ __forceinline__ void combo(float& DZ, float& WLIQ, float& WICE, float
 __device__ __forceinline__ void combine_body(SnowPack& s, float dzsoil1, int& ISNOW, float& soilwat1,
                                              float& soilice1, float& snowh, float& sneqv, float& PONDING1,
                                              float& PONDING2) {
-#define L(k) ((k) + 2)
+#define L(k) NMP_CHK((k) + 2, 0, 2, 1)
   int ISNOW_OLD = ISNOW;
 
   for (int J = ISNOW_OLD + 1; J <= 0; ++J) {                                              // func:5276-5318
@@ -146,10 +146,10 @@ __device__ __noinline__ void divide(SnowPack& s) {
   int MSNO = -ISNOW;
   for (int J = 1; J <= NSNOW; ++J) {                                                      // func:5443-5450
     if (J <= MSNO) {
-      DZ[J - 1] = s.dz[J + ISNOW + 2];
-      SWICE[J - 1] = s.ice[J + ISNOW + 2];
-      SWLIQ[J - 1] = s.liq[J + ISNOW + 2];
-      TSNO[J - 1] = s.t[J + ISNOW + 2];
+      DZ[NMP_CHK(J - 1, 0, 2, 2)] = s.dz[NMP_CHK(J + ISNOW + 2, 0, 2, 2)];
+      SWICE[NMP_CHK(J - 1, 0, 2, 2)] = s.ice[NMP_CHK(J + ISNOW + 2, 0, 2, 2)];
+      SWLIQ[NMP_CHK(J - 1, 0, 2, 2)] = s.liq[NMP_CHK(J + ISNOW + 2, 0, 2, 2)];
+      TSNO[NMP_CHK(J - 1, 0, 2, 2)] = s.t[NMP_CHK(J + ISNOW + 2, 0, 2, 2)];
     }
   }
   if (MSNO == 1) {                                                                        // func:5454-5466
@@ -195,10 +195,10 @@ __device__ __noinline__ void divide(SnowPack& s) {
   ISNOW = -MSNO;                                                                          // func:5519-5526
   s.isnow = ISNOW;
   for (int J = ISNOW + 1; J <= 0; ++J) {
-    s.dz[J + 2] = DZ[J - ISNOW - 1];
-    s.ice[J + 2] = SWICE[J - ISNOW - 1];
-    s.liq[J + 2] = SWLIQ[J - ISNOW - 1];
-    s.t[J + 2] = TSNO[J - ISNOW - 1];
+    s.dz[NMP_CHK(J + 2, 0, 2, 2)] = DZ[NMP_CHK(J - ISNOW - 1, 0, 2, 2)];
+    s.ice[NMP_CHK(J + 2, 0, 2, 2)] = SWICE[NMP_CHK(J - ISNOW - 1, 0, 2, 2)];
+    s.liq[NMP_CHK(J + 2, 0, 2, 2)] = SWLIQ[NMP_CHK(J - ISNOW - 1, 0, 2, 2)];
+    s.t[NMP_CHK(J + 2, 0, 2, 2)] = TSNO[NMP_CHK(J - ISNOW - 1, 0, 2, 2)];
   }
 }
 
@@ -247,8 +247,8 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
                                       float elai, float esai, float fveg, float QVAP, float QDEW,
                                       const float (&FICEOLD)[3], float (&soilice)[4], float (&DZSNSO)[7],
                                       WaterResult& w) {
-  const float* VG = &T.veg[(c.lutyp - 1) * NVEGF];
-  const float* SP = &T.soil[(c.sltyp - 1) * NSOILP];
+  const float* VG = &T.veg[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGF];
+  const float* SP = &T.soil[NMP_CHK(c.sltyp - 1, 0, MAXSOILTYP - 1, 4) * NSOILP];
   const float DT = rc.dt;
   const float SMCMAX = SP[P_SMCMAX], BEXP = SP[P_BEXP];
   const int ISURBAN = T.flags[0];
@@ -538,7 +538,7 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
   if (c.ISNOW == 0) qinsrf = qinsrf + (QSNBOT + QSDEW + QRAIN) * 0.001f;
   else qinsrf = qinsrf + (QSNBOT + QSDEW) * 0.001f;
   QSEVA = QSEVA * 0.001f;                                                                 // func:4766
-  const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
+  const int NROOT = T.vegi[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGI + VI_NROOT];
   float ETRANI[4];
   static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     ETRANI[IX4(k)] = (k <= NROOT) ? w.ETRAN * e.BTRANI[IX4(k)] * 0.001f : 0.0f;
@@ -697,7 +697,7 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
         } else {
           DENOM = (rc.zsoil[k - 2 >= 0 ? k - 2 : 0] - rc.zsoil[k - 1]);
           if (opt.run == 1 || opt.run == 2) QDRAIN = 0.0f;
-          if (opt.run == 3) QDRAIN = T.gen[G_SLOPE + c.slptyp - 1] * WCND[IX4(k)];
+          if (opt.run == 3) QDRAIN = T.gen[G_SLOPE + NMP_CHK(c.slptyp - 1, 0, NGEN - G_SLOPE - 1, 4)] * WCND[IX4(k)];
           if (opt.run == 4) QDRAIN = (1.0f - FCRMAX) * WCND[IX4(k)];
           WFLUX = -(WDF[IX4(k > 1 ? k - 1 : k)] * dsmdz_prev) - WCND[IX4(k > 1 ? k - 1 : k)] + ETRANI[IX4(k)] + QDRAIN;
           AI[IX4(k)] = -WDF[IX4(k > 1 ? k - 1 : k)] * ddz_prev / DENOM;
@@ -804,17 +804,17 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
       });
       const float QDIS = (1.0f - FCRMAX) * 5.0f * m_expf(-T.gen[G_TIMEAN]) * m_expf(-6.0f * (c.ZWT - 2.0f));  // func:6557
 #ifdef NMP_FAST_ALGEBRA   // the fast build keeps this power in fp32, but with libdevice's accurate routine (not the MUFU pair)
-      const float S_NODEf = fmax2(fmin2(1.0f, pick(SMCg, IWT - 1) / SMCMAX), 0.01f);
+      const float S_NODEf = fmax2(fmin2(1.0f, pick(SMCg, IWT - 1, 6) / SMCMAX), 0.01f);
       float SMPFZ = -((SP[P_PSISAT] * 1000.0f) * m_accpowf(S_NODEf, -BEXP));
 #else
-      double S_NODE = (double)fmin2(1.0f, pick(SMCg, IWT - 1) / SMCMAX);                  // func:6560-6563 (fp64 island)
+      double S_NODE = (double)fmin2(1.0f, pick(SMCg, IWT - 1, 6) / SMCMAX);                  // func:6560-6563 (fp64 island)
       const double S_MIN = (double)0.01f;
       S_NODE = S_NODE > S_MIN ? S_NODE : S_MIN;
       float SMPFZ = (float)(-((double)(SP[P_PSISAT] * 1000.0f) * pow(S_NODE, (double)(-BEXP))));
 #endif
       SMPFZ = fmax2(-120000.0f, 0.20f * SMPFZ);
-      const float KA = pick(HK, IWT - 1);
-      const float znode_iwt = pick(ZNODE, IWT - 1);
+      const float KA = pick(HK, IWT - 1, 6);
+      const float znode_iwt = pick(ZNODE, IWT - 1, 6);
       const float WH_ZWT = -c.ZWT * 1.0E3f;                                               // func:6568-6571
       const float WH = SMPFZ - znode_iwt * 1.0E3f;
       float QIN = -KA * (WH_ZWT - WH) / ((c.ZWT - znode_iwt) * 1.0E3f);
@@ -835,7 +835,7 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
           static_for<3, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
             if (k >= IWT + 2) WS = WS + epore[IX4(k)] * DZMM[IX4(k)];
           });
-          c.ZWT = -pick(rc.zsoil, IWT) - (c.WT - 0.2f * 1000.0f * 25.0f - WS) / (pick(epore, IWT)) / 1000.0f;
+          c.ZWT = -pick(rc.zsoil, IWT, 6) - (c.WT - 0.2f * 1000.0f * 25.0f - WS) / (pick(epore, IWT, 6)) / 1000.0f;
         }
         float WTSUB = 0.0f;                                                               // func:6599-6606
         static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
@@ -874,19 +874,19 @@ __device__ __forceinline__ void water(const Opt& opt, const Tables& T, const Run
 // =====================================================================================================
 __device__ __forceinline__ void carbon(const Tables& T, const RunConst& rc, Column& c, const float (&DZSNSO)[7],
                                     float PSN, float BTRAN, float IGS, float& GPP, float& NPP, float& NEE) {
-  const float* VG = &T.veg[(c.lutyp - 1) * NVEGF];
+  const float* VG = &T.veg[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGF];
   const float DT = rc.dt;
   if ((c.lutyp == T.flags[1]) || (c.lutyp == T.flags[2]) || (c.lutyp == T.flags[3]) || (c.lutyp == T.flags[0])) {
     c.LAI = 0.0f; c.SAI = 0.0f; GPP = 0.0f; NPP = 0.0f; NEE = 0.0f;                       // func:6709-6726
     c.LFMASS = 0.0f; c.RTMASS = 0.0f; c.STMASS = 0.0f; c.WOOD = 0.0f; c.STBLCP = 0.0f; c.FASTCP = 0.0f;
     return;
   }
-  const float SMCMAX = T.soil[(c.sltyp - 1) * NSOILP + P_SMCMAX];
+  const float SMCMAX = T.soil[NMP_CHK(c.sltyp - 1, 0, MAXSOILTYP - 1, 4) * NSOILP + P_SMCMAX];
   const float LAPM = VG[V_SLA] / 1000.0f;
   const float WSTRES = 1.0f - BTRAN;
-  const int NROOT = T.vegi[(c.lutyp - 1) * NVEGI + VI_NROOT];
+  const int NROOT = T.vegi[NMP_CHK(c.lutyp - 1, 0, MAXVEGTYP - 1, 4) * NVEGI + VI_NROOT];
   float WROOT = 0.0f;
-  const float zroot = -pick(rc.zsoil, NROOT - 1);
+  const float zroot = root_depth(rc, NROOT);
   static_for<1, NSOIL>([&](auto k_) { constexpr int k = decltype(k_)::value;
     if (k <= NROOT) WROOT = WROOT + c.SMC[IX4(k)] / SMCMAX * DZSNSO[IX7(k)] / zroot;
   });

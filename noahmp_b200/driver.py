@@ -313,7 +313,8 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
         nsteps += g
         if F.is_boundary(t, cfg.begdatetime, out_freq):
             tic = _time.perf_counter()
-            full = gather_columns(diag, ntot).cpu().numpy()
+            full = gather_columns(diag, ntot)
+            full = full.cpu().numpy() if rank == 0 else None      # only the writing rank brings the planes to the host
             timing["gather_s"] += _time.perf_counter() - tic
             tic = _time.perf_counter()
             if as_nc:
@@ -331,7 +332,8 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
             diag[L.ACC_DIAG_PLANES[0]:] = 0.0   # ACCPRCP ... UGDRNOFF accumulate from one output to the next
         if F.is_boundary(t, cfg.begdatetime, res_freq):
             tic = _time.perf_counter()
-            full = gather_columns(state, ntot).cpu().numpy()
+            full = gather_columns(state, ntot)
+            full = full.cpu().numpy() if rank == 0 else None
             timing["gather_s"] += _time.perf_counter() - tic
             tic = _time.perf_counter()
             if as_nc:

@@ -185,6 +185,16 @@ class NoahMP:
         self._check(self.lib.noahmp_kernel_info(self.ctx, info), "noahmp_kernel_info")
         return {"registers": info[0], "local_bytes": info[1], "static_smem": info[2], "max_threads": info[3]}
 
+    def debug_bounds(self, reset: bool = False) -> dict:
+        """Counts of the device-side index checks of a ``-DNMP_BOUNDS`` library (``fast="bounds"``); ``checked`` is False for
+        every other build."""
+        hits, sites = C.c_ulonglong(0), C.c_uint(0)
+        rc = self._check(self.lib.noahmp_debug_bounds(self.ctx, C.byref(hits), C.byref(sites), int(reset)), "noahmp_debug_bounds")
+        return {"checked": rc == 1, "hits": int(hits.value), "sites": int(sites.value)}
+
+    def debug_bounds_selftest(self, idx: int) -> bool:
+        return self._check(self.lib.noahmp_debug_bounds_selftest(self.ctx, int(idx)), "noahmp_debug_bounds_selftest") == 1
+
     def close(self) -> None:
         if getattr(self, "ctx", None) is not None and self.ctx:
             self.lib.noahmp_finalize(self.ctx)

@@ -111,19 +111,19 @@ class RecordReader:
         t1 = t0 if w == 0.0 else t0 + dt.timedelta(seconds=n)
         return t0, t1, w
 
-    def load(self, t: dt.datetime) -> np.ndarray:
-        """The record of time ``t`` as a host array float32 [8][ncol] (no caching)."""
+    def load(self, t: dt.datetime, columns: slice | None = None) -> np.ndarray:
+        """The record of time ``t`` as a host array float32 [8][ncol] (no caching); with ``columns`` only that block of
+        columns, read through a memory map so that a rank of a multi-GPU run touches its own part of the file only."""
         p = self.path(t)
         if not os.path.isfile(p):
             raise FileNotFoundError(f"ERR: Unable to find forcing record {p}")
         if p.endswith(".npy"):
-            a = np.load(p)
-        else:
-            from . import ncio
-            a = ncio.read_record(p, self.ncol)
-        if a.shape != (len(RECORD_VARS), self.ncol) or a.dtype != np.float32:
-            raise ValueError(f"{p}: expected float32 [{len(RECORD_VARS)}][{self.ncol}], got {a.dtype} {a.shape}")
-        return a
+            a = np.load(p, mmap_mode="r" if columns is not None else None)
+            if a.shape != (len(RECORD_VARS), self.ncol) or a.dtype != np.float32:
+                raise ValueError(f"{p}: expected float32 [{len(RECORD_VARS)}][{self.ncol}], got {a.dtype} {a.shape}")
+            return np.ascontiguousarray(a[:, columns]) if columns is not None else a
+        from . import ncio
+        return ncio.read_record(p, self.ncol, columns)
 
     def record(self, t: dt.datetime):
         import torch
@@ -160,9 +160,9 @@ class RecordRing:
             free.append(self.held.pop(key))
         for key, t in need.items():
             if key not in self.held:
-                a = self.reader.load(t)[:, self.columns]
+                a = self.reader.load(t, self.columns)
                 slot = free.pop()
-                self.ring[slot].copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=False)
+                self.ring[slot].copy_(torch.from_numpy(a), non_blocking=False)
                 self.held[key] = slot
                 self.loads += 1
         return {t: self.held[stamp(t)] for t in times}

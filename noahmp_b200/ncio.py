@@ -125,18 +125,30 @@ def read_init(path: str, static_path: str | None = None) -> InitData:
     return out
 
 
-def read_record(path: str, ncol: int) -> np.ndarray:
-    """One forcing record as float32 [8][ncol] in the order of ``forcing.RECORD_VARS``."""
-    rec = np.empty((len(FORCING_ALIASES), ncol), f32)
-    with _open(path) as nc:
+def read_record(path: str, ncol: int, columns: slice | None = None) -> np.ndarray:
+    """One forcing record as float32 [8][ncol] in the order of ``forcing.RECORD_VARS``; with ``columns`` only that block of
+    the flattened grid, [8][columns.stop - columns.start] (a rank of a multi-GPU run reads its own columns: the file is
+    memory-mapped and only the pages of the block are touched)."""
+    from scipy.io import netcdf_file
+    width = ncol if columns is None else columns.stop - columns.start
+    rec = np.empty((len(FORCING_ALIASES), width), f32)
+    nc = netcdf_file(path, "r", mmap=columns is not None, version=2)
+    try:
         for i, names in enumerate(FORCING_ALIASES):
             name = next((n for n in names if n in nc.variables), None)
             if name is None:
                 raise ValueError(f"ERR: {path} has none of {names}")
-            a, _ = _squeeze_time(nc.variables[name])
-            if a.size != ncol:
-                raise ValueError(f"{path}: {name} has {a.size} cells, the run has {ncol} columns")
-            rec[i] = a.reshape(-1)
+            v = nc.variables[name]
+            if int(np.prod(v.shape)) != ncol:
+                raise ValueError(f"{path}: {name} has {int(np.prod(v.shape))} cells, the run has {ncol} columns")
+            flat = v.data.reshape(-1)           # a view (of the memory map when mapped): C order = the flattened grid
+            rec[i] = flat if columns is None else flat[columns]
+            del flat, v
+    finally:
+        try:
+            nc.close()
+        except Exception:   # scipy refuses to unmap while a view is alive; the copies above hold none
+            pass
     return rec
 
 

@@ -63,11 +63,14 @@ def gather_columns(local, ncol: int, group=None):
         return local
     world = dist.get_world_size(group)
     per = (ncol + world - 1) // world
-    pad = torch.zeros((local.shape[0], per), dtype=local.dtype, device=local.device)
-    pad[:, :local.shape[1]] = local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
-    return torch.cat(parts, dim=1)[:, :ncol].contiguous()
+    if local.shape[1] == per:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros((local.shape[0], per), dtype=local.dtype, device=local.device)
+        pad[:, :local.shape[1]] = local
+    out = torch.empty((world * pad.shape[0], per), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)     # one collective into one buffer: rank-major [world * P][per]
+    return out.view(world, pad.shape[0], per).permute(1, 0, 2).reshape(local.shape[0], world * per)[:, :ncol].contiguous()
 
 
 def budget_means(budget, nsteps: int) -> dict:
