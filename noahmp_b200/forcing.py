@@ -121,7 +121,7 @@ class RecordReader:
             a = np.load(p, mmap_mode="r" if columns is not None else None)
             if a.shape != (len(RECORD_VARS), self.ncol) or a.dtype != np.float32:
                 raise ValueError(f"{p}: expected float32 [{len(RECORD_VARS)}][{self.ncol}], got {a.dtype} {a.shape}")
-            return np.ascontiguousarray(a[:, columns]) if columns is not None else a
+            return np.array(a[:, columns]) if columns is not None else a      # a copy: the map is read-only
         from . import ncio
         return ncio.read_record(p, self.ncol, columns)
 
