@@ -224,6 +224,61 @@ def cpu_baseline(w, sample_cols: int, fast: bool = True, repeats: int = 1) -> di
                       f"({'-O3 AVX2+FMA' if fast else '-O2 no-FMA'} build of the C++ restatement, OpenMP static, {best:.2f} s)"}
 
 
+def cpu_leg_of(name: str, variant: str, local: int, sample_cols: int = 20_000, max_steps: int = 48) -> dict:
+    """CPU figure and iteration-count check of one BASELINE config on a bounded sample (part of the cpu_baseline leg: the
+    oracle is the thing timed, and the checker of the counters).  (1) the -O3 port on all host cores on `sample_cols` columns
+    x min(steps, max_steps) model steps; (2) north star "identical iteration counts in the energy-balance solver": from the
+    SAME state (the plain oracle's after all but the last of those steps) one more step by the plain oracle and by the GPU
+    build, packed counters compared per column - canopy Newton loop (func:2870-2875), stomata bisections (func:3830-3842),
+    soil sub-steps (func:5971-5978).  The exit tests sit on fp32 values that differ in the last ulps between any two libm
+    implementations, so the yardstick is printed beside it: the same comparison between two CPU builds of the oracle."""
+    import torch
+    from oracle.oracle import Oracle
+    from noahmp_b200.engine import NoahMP
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import accuracy as A
+    ncol_full, nsteps_full = {"single": (1, 96), "uniform100k": (100_000, 48), "global025": (280_000, 8760),
+                              "conus1km": (17_000_000, 24), "snow1m": (1_000_000, 720)}[name]
+    n, nsteps = min(sample_cols, ncol_full), min(max_steps, nsteps_full)
+    w = synth.make_workload(name, ncol=n, nsteps=nsteps)
+    forcing = synth.forcing_all(w)
+    tables = ParamTables.default()
+    st = w.state.copy()
+    t0 = time.perf_counter()
+    Oracle(tables, w.opts, fast="fast").run_workload(w, forcing, state=st, nthreads=host_threads())
+    dt = time.perf_counter() - t0
+    out = {"value": n * nsteps / dt, "unit": UNIT, "cores": host_threads(), "kind": "port",
+           "sample": f"{n} columns x {nsteps} model steps of {name} (-O3 AVX2+FMA build, OpenMP static, {dt:.2f} s)"}
+    if n < 64 or nsteps < 2:
+        return out
+    kw = dict(dt=w.dt, zsoil=synth.ZSOIL, yearlen=w.yearlen, zref=w.zref, co2_frac=w.co2_frac, o2_frac=w.o2_frac, foln=w.foln)
+    s0 = w.state.copy()
+    Oracle(tables, w.opts, fast=False).run(s0, np.ascontiguousarray(forcing[:-1]), w.static_f, w.static_i, julian0=w.julian0,
+                                           nthreads=host_threads(), **kw)
+    jlast = w.julian0 + (nsteps - 1) * w.dt / 86400.0
+    last = np.ascontiguousarray(forcing[-1:])
+
+    def cpu_step(kind):
+        s, d = s0.copy(), np.zeros((L.NDIAG, n), np.float32)
+        Oracle(tables, w.opts, fast=kind).run(s, last, w.static_f, w.static_i, julian0=jlast, diag=d, nthreads=host_threads(), **kw)
+        return d[L.D["ITER"]]
+
+    it_ref = cpu_step(False)
+    dev = torch.device("cuda", local)
+    eng = NoahMP(tables, w.opts, device=local, fast=variant)
+    dg = torch.zeros((L.NDIAG, n), dtype=torch.float32, device=dev)
+    eng.run(eng.run_params(w.dt, synth.ZSOIL, jlast, w.yearlen, w.zref, w.co2_frac, w.o2_frac, w.foln), torch.from_numpy(s0.copy()).to(dev),
+            torch.from_numpy(last).to(dev), torch.from_numpy(w.static_f).to(dev), torch.from_numpy(w.static_i).to(dev), dg, None)
+    torch.cuda.synchronize()
+    it_gpu = dg[L.D["ITER"]].cpu().numpy()
+    eng.close()
+    out["iteration_count_mismatch"] = {"gpu_vs_oracle": A.iteration_mismatch(it_gpu, it_ref),
+                                       "two_cpu_builds_of_the_oracle": A.iteration_mismatch(cpu_step("fast"), it_ref),
+                                       "columns": n, "after_steps": nsteps - 1,
+                                       "what": "fraction of columns whose counter differs on one step taken from identical states"}
+    return out
+
+
 def translated_reference_leg(w, sample_cols: int = 200_000):
     """The reference's own statements (mechanical Fortran -> C++ translation, oracle/_ref, -O2, OpenMP over columns) timed on a
     smaller sample.  It is about half as fast as the hand-written port, so the port stays the baseline the GPU is set against
@@ -715,6 +770,14 @@ def run_ours(args):
             tr = translated_reference_leg(w)
             if tr:
                 line["cpu_baseline"]["translated_reference"] = tr
+            if w.name == "conus1km" and args.ncol is None and not args.no_other_workloads:
+                per = {}
+                for name in ("single", "uniform100k", "global025", "conus1km", "snow1m"):
+                    try:
+                        per[name] = cpu_leg_of(name, args.variant, local)
+                    except Exception as exc:  # pragma: no cover - a CPU leg must never take the line down
+                        per[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                line["cpu_baseline"]["per_config"] = per
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = None
         emit(line)

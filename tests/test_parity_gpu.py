@@ -115,13 +115,30 @@ def test_strict_matches_committed_golden(tables, name):
 
 
 # ---------------------------------------------------------------------------------------------- tier 2
-TOL_PLANES = ["TV", "TG", "STC+1", "STC+2", "STC+3", "STC+4", "SMC1", "SMC2", "SMC3", "SMC4", "SOILWAT1", "SOILWAT4", "ZWT",
-              "WA", "WT", "SNEQV", "SNOWH", "ALBOLD"]
+import accuracy as A  # noqa: E402  (tools/accuracy.py: the tolerance-unit instrument of the full-length tests)
+
+FLOAT_PLANES = [L.STATE[p] for p in A.FLOAT_PLANES]     # all 43 fp32 planes of the live state (ISNOW is compared exactly)
 
 
 def frac_within(a, b, rel=1e-4, floor=1e-6):
     d = np.abs(a.astype(np.float64) - b.astype(np.float64))
     return float(((d <= rel * np.maximum(np.abs(a), np.abs(b))) | (d <= floor)).mean())
+
+
+def assert_every_plane(gs, cs, ys, bar, cols=None, slack=0.02, rel=1e-4, planes=None):
+    """Every fp32 plane of the live state: the fraction of columns inside the north star's tolerance (rel 1e-4, abs floor 1e-6)
+    must reach `bar`, or come within `slack` of what a second, equally valid CPU evaluation of the same source reaches (`ys`:
+    the oracle rebuilt with FMA contraction) - the canopy Newton loop and the layer thresholds amplify last-ulp differences
+    between ANY two evaluations, and the planes they feed (FWET, CANLIQ, QSNOW, the snow layers) show it first."""
+    sel = slice(None) if cols is None else cols
+    bad = []
+    for name in (planes or FLOAT_PLANES):
+        p = L.S[name]
+        fg = frac_within(cs[p][sel], gs[p][sel], rel)
+        fy = frac_within(cs[p][sel], ys[p][sel], rel)
+        if fg < min(bar, fy - slack):
+            bad.append((name, round(fg, 4), round(fy, 4)))
+    assert not bad, f"planes below the bar (plane, GPU build, second CPU build): {bad}"
 
 
 @pytest.mark.parametrize("variant", ["parity", "fast"])
@@ -137,10 +154,8 @@ def test_default_builds_within_tolerance(tables, oracle_libs, variant, workload,
     assert cflag == 0 and int(gb[L.B["NFLAGGED"]]) == 0
     isn_ok = gs[L.S["ISNOW"]].view(np.int32) == cs[L.S["ISNOW"]].view(np.int32)
     assert isn_ok.mean() >= 0.999
-    bar = 0.97 if workload == "snow1m" else 0.99
-    for p in TOL_PLANES:
-        fr = frac_within(cs[L.S[p]][isn_ok], gs[L.S[p]][isn_ok])
-        assert fr >= bar, f"{p}: only {fr:.4f} of columns within rel 1e-4"
+    ys, _, _ = cpu_run(tables, w, forcing, "fast")
+    assert_every_plane(gs, cs, ys, 0.97 if workload == "snow1m" else 0.99, cols=isn_ok)
     it_c, it_g = cd[L.D["ITER"]].view(np.int32) & 0xff, gd[L.D["ITER"]].view(np.int32) & 0xff
     assert (it_c == it_g).mean() >= 0.95
     assert ((cd[L.D["ITER"]].view(np.int32) >> 24) == (gd[L.D["ITER"]].view(np.int32) >> 24)).mean() >= 0.999
@@ -217,9 +232,9 @@ REF_CASES = {c[0]: c for c in make_reference_golden.CASES}
 @pytest.mark.parametrize("name", list(REF_CASES))
 def test_gpu_against_reference_fixtures(tables, variant, name):
     """tests/golden/ref_*.npz = outputs of the reference's source (mechanical translation, tools/make_reference_golden.py).
-    Every GPU build, every workload, every option value: layer count exact, prognostic state inside the north star's
-    1e-4 (abs floor 1e-6) for >= 95 % of the columns of each plane (>= 90 % on the 64-column option cases: the canopy
-    Newton loop amplifies last-ulp libm differences in a handful of columns, as it does between two CPU builds)."""
+    Every GPU build, every workload, every option value: layer count exact, EVERY fp32 plane of the live state inside the
+    north star's 1e-4 (abs floor 1e-6) for >= 95 % of the columns (>= 90 % on the 64-column option cases), or within 3 (5)
+    points of what the FMA-contracted CPU build of the oracle reaches on that plane (assert_every_plane)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.npz"))
     w, opts = make_reference_golden.case_workload(name)
     ncol = w.ncol
@@ -227,29 +242,27 @@ def test_gpu_against_reference_fixtures(tables, variant, name):
     assert int(gb[L.B["NFLAGGED"]]) == 0
     isn_same = (gs[L.S["ISNOW"]].view(np.int32) == g["state"][L.S["ISNOW"]].view(np.int32)).mean()
     assert isn_same >= (0.98 if ncol >= 128 else 0.95), isn_same
-    floor = 0.95 if ncol >= 128 else 0.90
-    for nm in TOL_PLANES:
-        ok = frac_within(gs[L.S[nm]], g["state"][L.S[nm]], rel=1e-4 if ncol > 1 else 1e-3)
-        assert ok >= floor, (nm, ok)
+    # yardstick: the CPU oracle (which reproduces the fixture bit for bit in its plain build) rebuilt with FMA contraction
+    ys = w.state.copy()
+    Oracle(tables, opts, fast="fast").run_workload(w, synth.forcing_all(w), state=ys)
+    assert_every_plane(gs, g["state"], ys, 0.95 if ncol >= 128 else 0.90, slack=0.03 if ncol >= 128 else 0.05,
+                       rel=1e-4 if ncol > 1 else 1e-3)
 
 
 @pytest.mark.parametrize("variant", ["strict", "parity", "fast"])
 @pytest.mark.parametrize("name", make_reference_golden.FP64_CASES)
 def test_gpu_error_against_the_fp64_twin(tables, variant, name):
-    """Distance to the fp64 evaluation of the reference's statements (tests/golden/ref64_*.npz): a GPU build may be at most
-    4x as far from it as the fp32 reference itself is (95th percentile over columns per slow plane, floor 2e-6 relative)."""
+    """Distance to the fp64 evaluation of the reference's statements (tests/golden/ref64_*.npz), every fp32 plane of the live
+    state: inside the tolerance, or no further from the twin than K x the fp32 reference itself is (K = 4, 4, 8, 32 at the
+    median, 95th, 99.9th percentile and maximum over the columns; tools/accuracy.py)."""
     g32 = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_{name}.npz"))["state"]
     g64 = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref64_{name}.npz"))["state"]
     w, opts = make_reference_golden.case_workload(name)
     gs, _, _ = gpu_run(tables, w, synth.forcing_all(w), variant)
 
-    def q95(a, b):
-        a, b = a.astype(np.float64), b.astype(np.float64)
-        return float(np.quantile(np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-3), 0.95))
-    for nm in ["TG", "TV", "STC+1", "STC+4", "SMC1", "SMC4", "SOILWAT1", "ZWT", "WA", "SNEQV", "SNOWH"]:
-        p = L.S[nm]
-        ours, theirs = q95(gs[p], g64[p]), q95(g32[p], g64[p])
-        assert ours <= 4.0 * theirs + 2e-6, (nm, ours, theirs)
+    # all 43 fp32 planes, median / 95th / 99.9th percentile / maximum over the columns, in tolerance units (tools/accuracy.py)
+    cmp = A.compare(gs[:L.NSTATE_CORE], g32[:L.NSTATE_CORE], g64[:L.NSTATE_CORE])
+    assert cmp["pass"], "\n" + A.table(cmp) + f"\nworst: {cmp['worst']}"
 
 
 @pytest.mark.parametrize("name", ["special_global", "special_snow"])
