@@ -253,10 +253,12 @@ def cpu_leg_of(name: str, variant: str, local: int, sample_cols: int = 20_000, m
         return out
     kw = dict(dt=w.dt, zsoil=synth.ZSOIL, yearlen=w.yearlen, zref=w.zref, co2_frac=w.co2_frac, o2_frac=w.o2_frac, foln=w.foln)
     s0 = w.state.copy()
-    Oracle(tables, w.opts, fast=False).run(s0, np.ascontiguousarray(forcing[:-1]), w.static_f, w.static_i, julian0=w.julian0,
+    # the compared step is the sunniest one of the sample (the stomatal bisections only run by day)
+    m = int(np.argmax(forcing[1:, L.FORCING.index("COSZ")].mean(axis=1))) + 1
+    Oracle(tables, w.opts, fast=False).run(s0, np.ascontiguousarray(forcing[:m]), w.static_f, w.static_i, julian0=w.julian0,
                                            nthreads=host_threads(), **kw)
-    jlast = w.julian0 + (nsteps - 1) * w.dt / 86400.0
-    last = np.ascontiguousarray(forcing[-1:])
+    jlast = w.julian0 + m * w.dt / 86400.0
+    last = np.ascontiguousarray(forcing[m:m + 1])
 
     def cpu_step(kind):
         s, d = s0.copy(), np.zeros((L.NDIAG, n), np.float32)
@@ -274,7 +276,7 @@ def cpu_leg_of(name: str, variant: str, local: int, sample_cols: int = 20_000, m
     eng.close()
     out["iteration_count_mismatch"] = {"gpu_vs_oracle": A.iteration_mismatch(it_gpu, it_ref),
                                        "two_cpu_builds_of_the_oracle": A.iteration_mismatch(cpu_step("fast"), it_ref),
-                                       "columns": n, "after_steps": nsteps - 1,
+                                       "columns": n, "after_steps": m,
                                        "what": "fraction of columns whose counter differs on one step taken from identical states"}
     return out
 
