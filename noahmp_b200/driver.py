@@ -232,6 +232,54 @@ def read_restart(path: str):
     return z["state"].astype(f32), dt.datetime.strptime(str(z["time"]), "%Y%m%d%H%M"), int(z["step"])
 
 
+class _AsyncWriter:
+    """Output and restart files are written by a background thread of the writing rank: the planes go to a page-locked host
+    buffer with an asynchronous copy, and the time loop goes on while the thread waits for the copy and writes the file."""
+
+    def __init__(self, depth: int = 2):
+        import queue
+        import threading
+        self.q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self.busy_s, self.error = 0.0, None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        import time as _t
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            tic = _t.perf_counter()
+            try:
+                job()
+            except Exception as exc:      # reported by close(): a failed write must not pass silently
+                self.error = exc
+            self.busy_s += _t.perf_counter() - tic
+
+    def submit(self, planes_dev, write) -> None:
+        """``write(host_array)`` runs on the thread once ``planes_dev`` has arrived in host memory."""
+        import torch
+        host = torch.empty(planes_dev.shape, dtype=planes_dev.dtype, pin_memory=planes_dev.is_cuda)
+        host.copy_(planes_dev, non_blocking=True)
+        ev = None
+        if planes_dev.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+
+        def job(host=host, ev=ev, keep=planes_dev):
+            if ev is not None:
+                ev.synchronize()
+            write(host.numpy())
+        self.q.put(job)
+
+    def close(self) -> None:
+        self.q.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+
+
 # ------------------------------------------------------------------------------------------------
 def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_launch: int = 24) -> dict:
     """The file-driven time loop.  Forcing valid at the start of each step; launches are cut at output and restart
@@ -281,7 +329,15 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
     # interpolates them and computes COSZ in its own load - no prepared forcing planes, no preparation pass
     max_steps_per_launch = min(max_steps_per_launch, 32)
     reader = F.RecordReader(cfg.indir, cfg.infreq, cfg.begdatetime, ntot, dev)
-    ring = F.RecordRing(reader, max_steps_per_launch + 2, mine, dev)
+    # file reads run ahead of the time loop on a thread (page-locked buffers, asynchronous copies); NOAHMP_PREFETCH=0: inline
+    prefetch = None
+    if os.environ.get("NOAHMP_PREFETCH", "1") != "0":
+        prefetch = F.RecordPrefetcher(reader, mine, reader.bracket(t)[0], cfg.enddatetime)
+    ring = F.RecordRing(reader, max_steps_per_launch + 2, mine, dev, prefetch)
+    writer = _AsyncWriter() if rank == 0 else None
+    if world > 1:       # communicator set-up belongs to initialisation, not to the first output of the time loop
+        gather_columns(torch.zeros((1, ncol), dtype=torch.float32, device=dev), ntot)
+        torch.cuda.synchronize()
     nsteps, written = step0, []
     timing = {"ingest_s": 0.0, "launch_s": 0.0, "gather_s": 0.0, "write_s": 0.0}
     import time as _time
@@ -313,8 +369,7 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
         nsteps += g
         if F.is_boundary(t, cfg.begdatetime, out_freq):
             tic = _time.perf_counter()
-            full = gather_columns(diag, ntot)
-            full = full.cpu().numpy() if rank == 0 else None      # only the writing rank brings the planes to the host
+            full = gather_columns(diag, ntot)         # only the writing rank brings the planes to the host
             timing["gather_s"] += _time.perf_counter() - tic
             tic = _time.perf_counter()
             if as_nc:
@@ -324,16 +379,17 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
             if rank == 0:
                 os.makedirs(cfg.outdir, exist_ok=True)
                 if as_nc:
-                    ncio.write_output(p, full, t, cols.grid)
+                    writer.submit(full, lambda a, p=p, t=t: ncio.write_output(p, a, t, cols.grid))
                 else:
-                    np.savez(p, diag=full, planes=np.asarray(L.DIAG), time=F.stamp(t))
+                    writer.submit(full, lambda a, p=p, t=t: np.savez(p, diag=a, planes=np.asarray(L.DIAG), time=F.stamp(t)))
             written.append(p)
             timing["write_s"] += _time.perf_counter() - tic
             diag[L.ACC_DIAG_PLANES[0]:] = 0.0   # ACCPRCP ... UGDRNOFF accumulate from one output to the next
         if F.is_boundary(t, cfg.begdatetime, res_freq):
             tic = _time.perf_counter()
             full = gather_columns(state, ntot)
-            full = full.cpu().numpy() if rank == 0 else None
+            if world == 1:
+                full = full.clone()      # the one-rank gather is the state tensor itself, which the next launch advances
             timing["gather_s"] += _time.perf_counter() - tic
             tic = _time.perf_counter()
             if as_nc:
@@ -342,15 +398,24 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
                 p = os.path.join(cfg.resdir, "RESTART." + F.stamp(t) + ".npz")
             if rank == 0:
                 if as_nc:
-                    ncio.write_restart(p, full, t, nsteps, cols.grid)
+                    writer.submit(full, lambda a, p=p, t=t, k=nsteps: ncio.write_restart(p, a, t, k, cols.grid))
                 else:
-                    write_restart(p, full, t, nsteps)
+                    writer.submit(full, lambda a, p=p, t=t, k=nsteps: write_restart(p, a, t, k))
             written.append(p)
             timing["write_s"] += _time.perf_counter() - tic
     torch.cuda.synchronize()
+    tic = _time.perf_counter()
+    if writer is not None:
+        writer.close()                       # every file is on disk before the run reports
+        timing["writer_thread_busy_s"] = writer.busy_s
+    timing["write_s"] += _time.perf_counter() - tic
+    if prefetch is not None:
+        prefetch.close()
+        timing["reader_thread_busy_s"] = prefetch.busy_s
     timing["total_s"] = _time.perf_counter() - t_wall0
     timing["synchronised_per_launch"] = detail
     timing["records_loaded"] = ring.loads
+    timing["records_prefetched"] = ring.prefetched
     allreduce_budget(budget)
     out = _summary(gather_columns(state, ntot).cpu().numpy(), gather_columns(diag, ntot).cpu().numpy(), budget.cpu().numpy(), ntot,
                    nsteps, dtm.total_seconds(), cfg.physics_options())

@@ -136,17 +136,87 @@ class RecordReader:
         return self._cache[key]
 
 
+class RecordPrefetcher:
+    """Reads the records of a run ahead of the time loop, in time order, on a small pool of threads, into page-locked host
+    buffers (so that the copy to the device is asynchronous too).  The time loop takes them in the same order; anything
+    unexpected (a record asked for out of order, a missing file) makes :meth:`take` return None and the caller reads the
+    record itself, with the reader's own error messages."""
+
+    def __init__(self, reader: RecordReader, columns: slice, first: dt.datetime, last: dt.datetime, depth: int = 16,
+                 pinned: bool = True, threads: int = 4):
+        import collections
+        from concurrent.futures import ThreadPoolExecutor
+        import torch
+        self.reader, self.columns, self.depth = reader, columns, depth
+        n = columns.stop - columns.start
+        self.free = [torch.empty((len(RECORD_VARS), n), dtype=torch.float32, pin_memory=pinned) for _ in range(depth)]
+        self.pending: "collections.deque" = collections.deque()     # (stamp, future, buffer) in time order
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.busy_s = 0.0
+        self._dead = False
+        step = dt.timedelta(seconds=reader.freq[0])
+        self._times = iter([first + k * step for k in range(int((last - first) / step) + 1)])
+        self._fill()
+
+    def _load(self, t, buf):
+        import time
+        tic = time.perf_counter()
+        buf.numpy()[...] = self.reader.load(t, self.columns)
+        self.busy_s += time.perf_counter() - tic      # summed over the pool's threads
+        return buf
+
+    def _fill(self) -> None:
+        while self.free and not self._dead:
+            t = next(self._times, None)
+            if t is None:
+                return
+            buf = self.free.pop()
+            self.pending.append((stamp(t), self.pool.submit(self._load, t, buf), buf))
+
+    def take(self, key: str):
+        """The buffer holding record ``key`` (to be handed back with :meth:`give_back`), or None."""
+        while not self._dead and self.pending:
+            k, fut, buf = self.pending.popleft()
+            if k > key:                # the loop asked for an earlier record than the readers have reached: out of order
+                self.pending.appendleft((k, fut, buf))
+                self._dead = True
+                return None
+            try:
+                fut.result()
+            except Exception:          # missing / malformed file: the time loop reads it itself and reports
+                self._dead = True
+                return None
+            if k == key:
+                self._fill()
+                return buf
+            self.free.append(buf)      # a record the loop skipped
+            self._fill()
+        return None
+
+    def give_back(self, buf) -> None:
+        self.free.append(buf)
+        self._fill()
+
+    def close(self) -> None:
+        self._dead = True
+        self.pool.shutdown(wait=True, cancel_futures=True)
+
+
 class RecordRing:
     """Device ring of forcing records for records-driven launches (``noahmp_run_records``): a record is read from disk and
-    copied to the device once, however many model steps and launches it serves."""
+    copied to the device once, however many model steps and launches it serves.  With a :class:`RecordPrefetcher` the file
+    reads run ahead on a background thread and the copies are asynchronous (page-locked buffers)."""
 
-    def __init__(self, reader: RecordReader, slots: int, columns: slice, device):
+    def __init__(self, reader: RecordReader, slots: int, columns: slice, device, prefetch: "RecordPrefetcher | None" = None):
         import torch
         self.reader, self.columns = reader, columns
         n = columns.stop - columns.start
         self.ring = torch.empty((slots, len(RECORD_VARS), n), dtype=torch.float32, device=device)
         self.held: dict = {}      # stamp -> slot
         self.loads = 0
+        self.prefetch = prefetch
+        self.prefetched = 0
+        self._inflight: list = []  # (event, pinned buffer) of copies not yet known to be complete
 
     def slots_for(self, times) -> dict:
         """Make every record time in ``times`` resident; returns {time: slot}.  Slots of records this launch does not need
@@ -158,11 +228,28 @@ class RecordRing:
         free = [s for s in range(self.ring.shape[0]) if s not in self.held.values()]
         for key in [k for k in self.held if k not in need]:
             free.append(self.held.pop(key))
-        for key, t in need.items():
+        for ev, buf in [x for x in self._inflight if x[0].query()]:
+            self.prefetch.give_back(buf)
+        self._inflight = [x for x in self._inflight if not x[0].query()]
+        for key in sorted(need):          # time order: the order the prefetcher reads in
             if key not in self.held:
-                a = self.reader.load(t, self.columns)
                 slot = free.pop()
-                self.ring[slot].copy_(torch.from_numpy(a), non_blocking=False)
+                buf = self.prefetch.take(key) if self.prefetch is not None else None
+                if buf is not None:
+                    self.ring[slot].copy_(buf, non_blocking=True)
+                    if self.ring.is_cuda:
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        self._inflight.append((ev, buf))
+                        while len(self._inflight) > max(1, self.prefetch.depth - 3):   # never starve the reader of buffers
+                            ev0, buf0 = self._inflight.pop(0)
+                            ev0.synchronize()
+                            self.prefetch.give_back(buf0)
+                    else:
+                        self.prefetch.give_back(buf)
+                    self.prefetched += 1
+                else:
+                    self.ring[slot].copy_(torch.from_numpy(self.reader.load(need[key], self.columns)), non_blocking=False)
                 self.held[key] = slot
                 self.loads += 1
         return {t: self.held[stamp(t)] for t in times}

@@ -299,3 +299,28 @@ def test_equilibrium_water_table_invariants_and_no_drift(tmp_path, tables, oracl
     print("WA drift over 24 steps [mm], median / p95: equilibrium", np.median(drift["equilibrium"][m]), np.quantile(drift["equilibrium"][m], 0.95),
           " constant", np.median(drift["constant"][m]), np.quantile(drift["constant"][m], 0.95))
     assert np.quantile(drift["equilibrium"][m], 0.95) <= 0.25 * np.quantile(drift["constant"][m], 0.95)
+
+
+def test_record_prefetcher_delivers_what_the_reader_reads(tmp_path):
+    """The read-ahead pool (page-locked buffers on a GPU, plain ones here) hands the time loop the same records in the same
+    slots as the inline reader - when records are skipped, when the loop runs past the prefetch window, and when a file is
+    missing (the inline reader then raises with the reference's `ERR:` message)."""
+    import torch
+    ncol, t0 = 40, dt.datetime(2000, 7, 1)
+    rng = np.random.default_rng(8)
+    for h in range(20):
+        if h != 15:
+            np.save(tmp_path / (F.stamp(t0 + dt.timedelta(hours=h)) + ".npy"), rng.normal(280.0, 20.0, size=(8, ncol)).astype(np.float32))
+    rd = F.RecordReader(str(tmp_path), "1 hour", t0, ncol, "cpu")
+    cols = slice(5, 33)
+    pf = F.RecordPrefetcher(rd, cols, t0, t0 + dt.timedelta(hours=11), depth=4, pinned=False, threads=2)
+    a, b = F.RecordRing(rd, 5, cols, "cpu", prefetch=pf), F.RecordRing(rd, 5, cols, "cpu")
+    for k in (0, 1, 2, 4, 5, 8, 9, 10, 11, 12):        # 3, 6, 7 are skipped; 12.. lie past the window of the prefetcher
+        times = [t0 + dt.timedelta(hours=k + j) for j in range(3)]
+        sa, sb = a.slots_for(times), b.slots_for(times)
+        for t in times:
+            assert torch.equal(a.ring[sa[t]], b.ring[sb[t]])
+    assert a.loads == b.loads and 0 < a.prefetched < a.loads
+    with pytest.raises(FileNotFoundError, match="ERR: Unable to find forcing record"):
+        a.slots_for([t0 + dt.timedelta(hours=15)])
+    pf.close()
