@@ -125,30 +125,83 @@ def read_init(path: str, static_path: str | None = None) -> InitData:
     return out
 
 
-def read_record(path: str, ncol: int, columns: slice | None = None) -> np.ndarray:
-    """One forcing record as float32 [8][ncol] in the order of ``forcing.RECORD_VARS``; with ``columns`` only that block of
-    the flattened grid, [8][columns.stop - columns.start] (a rank of a multi-GPU run reads its own columns: the file is
-    memory-mapped and only the pages of the block are touched)."""
+_RECORD_LAYOUTS: dict = {}     # (header bytes, ncol) -> [(offset of the variable's data, dtype string)] in forcing.RECORD_VARS order
+
+
+def _record_layout(path: str, ncol: int):
+    """Parse one record file with scipy and remember where its eight variables start.  Files written by the same program
+    for the same grid have byte-identical headers, so the layout of the first record serves every later one whose header
+    compares equal (checked per file); anything else is parsed on its own."""
     from scipy.io import netcdf_file
-    width = ncol if columns is None else columns.stop - columns.start
-    rec = np.empty((len(FORCING_ALIASES), width), f32)
-    nc = netcdf_file(path, "r", mmap=columns is not None, version=2)
+    nc = netcdf_file(path, "r", mmap=True, version=2)
     try:
-        for i, names in enumerate(FORCING_ALIASES):
+        base = nc._mm_buf.__array_interface__["data"][0]
+        lay = []
+        for names in FORCING_ALIASES:
             name = next((n for n in names if n in nc.variables), None)
             if name is None:
                 raise ValueError(f"ERR: {path} has none of {names}")
             v = nc.variables[name]
             if int(np.prod(v.shape)) != ncol:
                 raise ValueError(f"{path}: {name} has {int(np.prod(v.shape))} cells, the run has {ncol} columns")
-            flat = v.data.reshape(-1)           # a view (of the memory map when mapped): C order = the flattened grid
-            rec[i] = flat if columns is None else flat[columns]
-            del flat, v
+            if v.isrec:
+                return None            # record variables are interleaved: leave those files to scipy
+            d = v.data
+            lay.append((d.__array_interface__["data"][0] - base, d.dtype.str))
+            del d, v
+    except AttributeError:             # scipy internals moved: no fast path
+        return None
     finally:
         try:
             nc.close()
-        except Exception:   # scipy refuses to unmap while a view is alive; the copies above hold none
+        except Exception:
             pass
+    return lay
+
+
+def read_record(path: str, ncol: int, columns: slice | None = None) -> np.ndarray:
+    """One forcing record as float32 [8][ncol] in the order of ``forcing.RECORD_VARS``; with ``columns`` only that block of
+    the flattened grid, [8][columns.stop - columns.start] (a rank of a multi-GPU run reads its own columns: the file is
+    memory-mapped and only the pages of the block are touched).  The header is parsed once per file layout, not per file."""
+    c0, c1 = (0, ncol) if columns is None else (columns.start, columns.stop)
+    rec = np.empty((len(FORCING_ALIASES), c1 - c0), f32)
+    with open(path, "rb") as fh:
+        head = fh.read(4096)
+    lay = None
+    for (hdr, n), cand in _RECORD_LAYOUTS.items():
+        if n == ncol and head.startswith(hdr):
+            lay = cand
+            break
+    if lay is None:
+        lay = _record_layout(path, ncol)
+        if lay is not None:
+            hlen = min(off for off, _ in lay)
+            if hlen <= len(head) and len(_RECORD_LAYOUTS) < 16:
+                _RECORD_LAYOUTS[(head[:hlen], ncol)] = lay     # the cell count was checked against this ncol
+    if lay is not None:
+        mm = np.memmap(path, dtype=np.uint8, mode="r")
+        try:
+            for i, (off, dts) in enumerate(lay):
+                item = np.dtype(dts).itemsize
+                if off + ncol * item > mm.size:
+                    raise ValueError(f"{path}: truncated (variable {FORCING_ALIASES[i][0]} ends beyond the file)")
+                rec[i] = mm[off + c0 * item: off + c1 * item].view(dts)
+        finally:
+            del mm
+        return rec
+    from scipy.io import netcdf_file                      # general path: let scipy interpret the file
+    nc = netcdf_file(path, "r", mmap=False, version=2)
+    try:
+        for i, names in enumerate(FORCING_ALIASES):
+            name = next((n for n in names if n in nc.variables), None)
+            if name is None:
+                raise ValueError(f"ERR: {path} has none of {names}")
+            a, _ = _squeeze_time(nc.variables[name])
+            if a.size != ncol:
+                raise ValueError(f"{path}: {name} has {a.size} cells, the run has {ncol} columns")
+            rec[i] = a.reshape(-1)[c0:c1]
+    finally:
+        nc.close()
     return rec
 
 

@@ -324,3 +324,41 @@ def test_record_prefetcher_delivers_what_the_reader_reads(tmp_path):
     with pytest.raises(FileNotFoundError, match="ERR: Unable to find forcing record"):
         a.slots_for([t0 + dt.timedelta(hours=15)])
     pf.close()
+
+
+def test_netcdf_record_layout_is_parsed_once_and_checked_per_file(tmp_path):
+    """`ncio.read_record` parses the header of the first record of a layout and reads the later ones at the remembered
+    offsets - only when their header compares equal; a file with another header is parsed on its own, a truncated one is
+    refused, and a rank's column block equals the same block of the whole record."""
+    from scipy.io import netcdf_file
+    from noahmp_b200 import ncio
+    rng = np.random.default_rng(12)
+
+    def write(name, ny, nx, order):
+        rec = rng.normal(280.0, 20.0, size=(8, ny * nx)).astype(np.float32)
+        names = ("T2D", "PSFC", "U2D", "V2D", "Q2D", "SWDOWN", "LWDOWN", "RAINRATE")
+        with netcdf_file(str(tmp_path / name), "w", version=2) as nc:
+            nc.createDimension("Time", 1)
+            nc.createDimension("south_north", ny)
+            nc.createDimension("west_east", nx)
+            for i in order:
+                v = nc.createVariable(names[i], "f4", ("Time", "south_north", "west_east"))
+                v[:] = rec[i].reshape(1, ny, nx)
+        return rec
+    ncio._RECORD_LAYOUTS.clear()
+    a = write("a.nc", 4, 6, range(8))
+    b = write("b.nc", 4, 6, range(8))                    # same layout: served from the cache
+    c = write("c.nc", 4, 6, reversed(range(8)))          # variables in another order: another header
+    d = write("d.nc", 3, 8, range(8))                    # same cell count on another grid: another header
+    for name, rec in (("a.nc", a), ("b.nc", b), ("c.nc", c), ("d.nc", d)):
+        got = ncio.read_record(str(tmp_path / name), 24)
+        assert np.array_equal(got.view(np.int32), rec.view(np.int32)), name
+        part = ncio.read_record(str(tmp_path / name), 24, slice(5, 17))
+        assert np.array_equal(part.view(np.int32), rec[:, 5:17].view(np.int32)), name
+    assert len(ncio._RECORD_LAYOUTS) == 3
+    blob = (tmp_path / "b.nc").read_bytes()
+    (tmp_path / "short.nc").write_bytes(blob[:-40])
+    with pytest.raises(ValueError, match="truncated"):
+        ncio.read_record(str(tmp_path / "short.nc"), 24)
+    with pytest.raises(ValueError, match="the run has 25 columns"):
+        ncio.read_record(str(tmp_path / "a.nc"), 25)
