@@ -152,10 +152,13 @@ def _record_layout(path: str, ncol: int):
     except AttributeError:             # scipy internals moved: no fast path
         return None
     finally:
-        try:
-            nc.close()
-        except Exception:
-            pass
+        import warnings
+        with warnings.catch_warnings():      # after an error a view of the map may still be alive: scipy warns and leaves it
+            warnings.simplefilter("ignore")  # to the garbage collector, which is fine for a read-only map
+            try:
+                nc.close()
+            except Exception:
+                pass
     return lay
 
 
