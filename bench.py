@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from noahmp_b200 import layout as L, synth  # noqa: E402
-from noahmp_b200.parallel import allreduce_budget, budget_means, divergence_order, shard  # noqa: E402
+from noahmp_b200.parallel import allreduce_budget, budget_means, device_for_rank, divergence_order, shard  # noqa: E402
 from noahmp_b200.tables import ParamTables  # noqa: E402
 
 B_ALG = 404  # algorithmic bytes per cell-step (SURVEY 8d / DESIGN.md section 4)
@@ -488,9 +488,10 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA GPU (no CPU fallback exists)")
+    local = device_for_rank(local_rank, world)       # the GPU of this rank (ranks are spread over the node's host bridges)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa(local)
@@ -754,6 +755,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": config_of(w, args, {
                     "columns_per_gpu": nloc, "variant": args.variant, "partition": f"block x{world}",
+                    "gpus": [device_for_rank(r, world) for r in range(world)],
                     "l2": "inputs larger than L2 (state+forcing per launch >> 126 MB); no flush needed"
                           if nloc * 4 * (2 * 44 + 9 * w.nsteps) > 2 * 126e6 else "inputs fit L2: traffic is L2-resident",
                     "kernel": eng.kernel_info()}),

@@ -290,10 +290,10 @@ def run_files(cfg, device: int | None = None, variant="fast", max_steps_per_laun
     the budget sums are all-reduced at the end."""
     import torch
     import torch.distributed as dist
-    from .parallel import allreduce_budget, gather_columns, shard
+    from .parallel import allreduce_budget, device_for_rank, gather_columns, shard
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0"))
+        device = device_for_rank(int(os.environ.get("LOCAL_RANK", "0")), world)
     dev = torch.device("cuda", device)
     own_group = False
     if world > 1 and not dist.is_initialized():

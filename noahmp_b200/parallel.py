@@ -17,6 +17,25 @@ def shard(ncol: int, rank: int, world: int) -> tuple[int, int]:
     return c0, min(c0 + per, ncol) - c0
 
 
+def device_for_rank(local_rank: int, world: int, ndev: int | None = None) -> int:
+    """GPU of this node for a local rank.  With as many visible GPUs as ranks: the rank itself.  With more GPUs than ranks
+    the ranks are spread over the node with a constant stride (4 ranks on 8 GPUs: 0, 2, 4, 6), so that they do not all sit
+    behind the same host bridge: on the 8 x B200 box measured (`profiles/r02_logs/r02_h2d_topology.jsonl`) four ranks copying
+    from pinned host memory get 115 GB/s together on GPUs 0-3 and 213 GB/s on GPUs 0, 2, 4, 6 - the step path has no
+    inter-GPU traffic, so the host link is the only placement concern.  ``NOAHMP_GPU_MAP=4,5,6,7`` overrides."""
+    import os
+    explicit = os.environ.get("NOAHMP_GPU_MAP")
+    if explicit:
+        m = [int(x) for x in explicit.split(",")]
+        return m[local_rank % len(m)]
+    if ndev is None:
+        import torch
+        ndev = torch.cuda.device_count()
+    if world <= 1 or ndev < 2 * world:
+        return local_rank
+    return local_rank * (ndev // world)
+
+
 def divergence_order(static_i, lat, world: int = 1, chunk: int = 32768):
     """Permutation of the columns that (a) groups them by divergence class -- land-use type (canopy tile on/off,
     table rows), then latitude band (day/night, phenology month) -- so the 32 lanes of a warp take the same

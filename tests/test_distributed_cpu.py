@@ -150,3 +150,17 @@ def test_gather_columns_rebuilds_the_block_partition():
     assert res == {0: True, 1: True}
     x = torch.ones(3, 7)
     assert gather_columns(x, 7) is x                            # no process group: identity
+
+
+def test_ranks_are_spread_over_the_gpus_of_a_node(monkeypatch):
+    """More GPUs than ranks: constant stride (the ranks do not share a host bridge); as many GPUs as ranks: identity;
+    NOAHMP_GPU_MAP overrides."""
+    from noahmp_b200.parallel import device_for_rank
+    monkeypatch.delenv("NOAHMP_GPU_MAP", raising=False)
+    assert [device_for_rank(r, 4, 8) for r in range(4)] == [0, 2, 4, 6]
+    assert [device_for_rank(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [device_for_rank(r, 8, 8) for r in range(8)] == list(range(8))
+    assert [device_for_rank(r, 4, 4) for r in range(4)] == [0, 1, 2, 3]
+    assert [device_for_rank(r, 2, 3) for r in range(2)] == [0, 1] and device_for_rank(0, 1, 8) == 0
+    monkeypatch.setenv("NOAHMP_GPU_MAP", "4,5,6,7")
+    assert [device_for_rank(r, 4, 8) for r in range(4)] == [4, 5, 6, 7]
