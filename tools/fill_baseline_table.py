@@ -21,6 +21,24 @@ def sci(x):
     return "—" if x is None else f"{x:.3g}".replace("e+0", "e").replace("e+", "e")
 
 
+def scaling_table(by_n) -> str:
+    """Section 6: device-timed and end-to-end scaling beside the measured host link."""
+    one = by_n[1]
+    out = ["| GPUs (which) | device-timed cell-steps/s | scaling | e2e cell-steps/s (partition) | e2e scaling | e2e, equal blocks | host link while all ranks copy, GB/s: "
+           "slowest rank x N / sum of the ranks' own rates | e2e x 32 B, GB/s |", "|---|---|---|---|---|---|---|---|"]
+    for n in sorted(by_n):
+        x = by_n[n]
+        e, h = x["e2e"], x["e2e"]["host_link"]
+        g = x["config"].get("gpus", list(range(n)))
+        eq = (e.get("equal_blocks") or {}).get("value")
+        part = "link-weighted" if eq else "equal"
+        rates = h.get("h2d_gbs_sum_while_all_copy")
+        out.append(f"| {n} ({', '.join(map(str, g))}) | {sci(x['value'])} | {x['value'] / one['value']:.2f}x | {sci(e['value'])} ({part}) | "
+                   f"{e['value'] / one['e2e']['value']:.2f}x | {sci(eq) if eq else 'same'} | {h['h2d_gbs_all_gpus']:.0f} / "
+                   f"{(f'{rates:.0f}' if rates else 'n/a')} | {e['value'] * 32 / 1e9:.0f} |")
+    return "\n".join(out)
+
+
 def main():
     argv = [a for a in sys.argv[1:] if a != "--write"]
     lines = [json.load(open(a)) for a in argv]
@@ -66,11 +84,17 @@ def main():
             "translated reference after the config's FULL step count; the figure in brackets is the fp32 reference's own distance "
             "from that twin.  `single` has one column: no percentile, no roofline.\n")
     print(table + "\n" + note)
+    scal = scaling_table(by_n) if len(by_n) > 1 and all(d.get("e2e") for d in by_n.values()) else None
+    if scal:
+        print(scal)
     if "--write" in sys.argv:
         p = os.path.join(ROOT, "BASELINE.md")
         s = open(p).read()
-        head = re.search(r"## 5\.[^\n]*\n", s)
-        s = s[:head.end()] + "\n" + table + "\n" + note
+        a, b = s.index("<!-- table5 -->"), s.index("<!-- /table5 -->")
+        s = s[:a] + "<!-- table5 -->\n" + table + "\n" + note + s[b:]
+        if scal and "<!-- table6 -->" in s:
+            a, b = s.index("<!-- table6 -->"), s.index("<!-- /table6 -->")
+            s = s[:a] + "<!-- table6 -->\n" + scal + "\n" + s[b:]
         open(p, "w").write(s)
 
 
