@@ -716,13 +716,16 @@ def run_ours(args):
         # becomes the headline `e2e` (the equal-block figure stays beside it); the device-timed `value` keeps equal blocks.
         rates = probe.get("h2d_gbs_each_rank_while_all_copy") or []
         if world > 1 and rates and max(rates) > 1.15 * min(rates):
-            try:
+            blk, err = None, None
+            try:     # preparation may fail on one rank (memory): the ranks agree below before any of them enters the leg
                 wsum = sum(rates)
                 edges = [0]
                 for r in range(world - 1):
                     edges.append(min(w.ncol, int(round(w.ncol * sum(rates[:r + 1]) / wsum / 256.0)) * 256))
                 edges.append(w.ncol)
                 c0w, nw = edges[rank], edges[rank + 1] - edges[rank]
+                if nw <= 0:
+                    raise ValueError("empty block")
                 wb = slice_workload(w, c0w, nw)
                 with torch.cuda.stream(stream):
                     st_w = torch.from_numpy(wb.state).to(dev)
@@ -743,15 +746,21 @@ def run_ours(args):
                 geo_w = torch.stack([sc_w[0], sc_w[1], torch.zeros_like(sc_w[0]), torch.ones_like(sc_w[0])]).contiguous()
                 del fo_w
                 torch.cuda.synchronize()
-                dt_w, launches_w, flagged_w, same_w = e2e_leg(st_w, rec_w, geo_w, sf_w, si_w, end_w)
+                blk = (st_w, rec_w, geo_w, sf_w, si_w, end_w)
+            except Exception as exc:  # pragma: no cover - the equal-block figure stands
+                err = f"{type(exc).__name__}: {exc}"
+            ready = torch.tensor([1 if blk is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ready, op=dist.ReduceOp.MIN)
+            if int(ready.item()) == 1:
+                dt_w, launches_w, flagged_w, same_w = e2e_leg(*blk)
                 equal = {k: e2e[k] for k in ("value", "gpu_launches", "flagged", "state_equals_resident_path")}
                 e2e.update({"value": w.ncol * w.nsteps * ne2e / dt_w, "gpu_launches": launches_w, "flagged": flagged_w,
                             "state_equals_resident_path": bool(same_w and same),
                             "partition": "blocks in proportion to each rank's measured host link",
                             "columns_per_rank": [edges[r + 1] - edges[r] for r in range(world)], "equal_blocks": equal})
-                del st_w, sf_w, si_w, sc_w, ids_w, end_w, rec_w, geo_w
-            except Exception as exc:  # pragma: no cover - the equal-block figure stands
-                e2e["link_weighted_error"] = f"{type(exc).__name__}: {exc}"
+            else:
+                e2e["link_weighted_error"] = err or "another rank could not prepare its block"
+            del blk
         # (2) full state round trip
         h_forcing = torch.empty((w.nsteps, L.NFORCING, nloc), dtype=torch.float32).pin_memory()
         h_forcing.copy_(forcing)
