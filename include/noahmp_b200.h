@@ -148,6 +148,25 @@ int64_t noahmp_advance_records_host(noahmp_ctx* ctx, const noahmp_run_params* rp
                                     const noahmp_step_forcing* steps, const float* geo_dev, const float* static_f_dev,
                                     const int32_t* static_i_dev, double* budget_host, int steps_per_launch);
 
+/* Zero suppression of record planes on their way through noahmp_advance_records_host.  Short-wave radiation is zero
+ * wherever it is night and precipitation wherever it is dry: before a record crosses the host link, host threads pack
+ * the candidate planes (bit q of plane_mask = plane q of a record; default SOLDN | PRCP = 0xA0, 0 = off) into a 32-column
+ * occupancy word + running count per group and the non-zero words themselves, and the step kernel's forcing load reads
+ * that form directly.  Lossless and bit-identical: only the bit pattern 0 is suppressed, a plane that is more than 80 %
+ * non-zero travels as it is.  host_threads <= 0: as many as the calling thread may run on, at most 8.  The reference has
+ * no counterpart (it has no forcing ingest at all; offline/noahmp_config.py:81-82 only names the record cadence). */
+int noahmp_set_record_packing(noahmp_ctx* ctx, unsigned plane_mask, int host_threads);
+
+/* The packer by itself (host only, no device needed; exported for tests): plane[ncol] -> occupancy[ceil(ncol/32)],
+ * before[ceil(ncol/32)] (non-zero words in earlier groups), values[<= ncol].  Returns the number of non-zero words. */
+int64_t noahmp_pack_plane(const float* plane, int64_t ncol, uint32_t* occupancy, uint32_t* before, float* values,
+                          int host_threads);
+
+/* Bytes the noahmp_advance_* entry points of this context have copied host -> device so far. */
+int64_t noahmp_h2d_bytes(const noahmp_ctx* ctx);
+/* Wall time (seconds) noahmp_advance_records_host has spent packing record planes on the host so far. */
+double noahmp_pack_seconds(const noahmp_ctx* ctx);
+
 /* ---- synthetic forcing generator (benchmark support; no counterpart in the reference) ------------
  * Fills forcing_dev [NFORCING][ncol] for one step with the hash-based generator of
  * noahmp_b200/synth.py (bit-identical).  sincos_dev [2][ncol] = sin(lat), cos(lat).

@@ -23,6 +23,7 @@ SYMBOLS = ["noahmp_init", "noahmp_finalize", "noahmp_set_stream", "noahmp_last_e
            "noahmp_set_tables", "noahmp_run", "noahmp_run_host", "noahmp_advance_host", "noahmp_run_records",
            "noahmp_advance_records_host", "noahmp_synth_forcing", "noahmp_synth_forcing_ids", "noahmp_prepare_forcing", "noahmp_layout",
            "noahmp_state_plane_name", "noahmp_forcing_plane_name", "noahmp_diag_plane_name", "noahmp_budget_name",
+           "noahmp_set_record_packing", "noahmp_pack_plane", "noahmp_h2d_bytes", "noahmp_pack_seconds",
            "noahmp_launch_count", "noahmp_kernel_info", "noahmp_debug_bounds", "noahmp_debug_bounds_selftest"]
 
 _cache: dict = {}
@@ -70,6 +71,13 @@ def load(fast=False) -> C.CDLL:
     for f in ("noahmp_state_plane_name", "noahmp_forcing_plane_name", "noahmp_diag_plane_name", "noahmp_budget_name"):
         getattr(lib, f).argtypes = [C.c_int]
         getattr(lib, f).restype = C.c_char_p
+    lib.noahmp_set_record_packing.argtypes = [vp, C.c_uint, C.c_int]
+    lib.noahmp_pack_plane.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int]
+    lib.noahmp_pack_plane.restype = C.c_int64
+    lib.noahmp_h2d_bytes.argtypes = [vp]
+    lib.noahmp_h2d_bytes.restype = C.c_int64
+    lib.noahmp_pack_seconds.argtypes = [vp]
+    lib.noahmp_pack_seconds.restype = C.c_double
     lib.noahmp_launch_count.argtypes = [vp]
     lib.noahmp_launch_count.restype = C.c_int64
     lib.noahmp_kernel_info.argtypes = [vp, ip]

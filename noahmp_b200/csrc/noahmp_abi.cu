@@ -2,12 +2,25 @@
 // the host-buffer entry point and the synthetic forcing generator.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/noahmp_b200.h"
 #include "column_step.cuh"
@@ -20,6 +33,64 @@ static_assert(NSTATE == NOAHMP_NSTATE && NSTATE_CORE == NOAHMP_NSTATE_CORE && NF
                   NGEN == NOAHMP_NGEN && NSOILP == NOAHMP_NSOILP && NCOLORP == NOAHMP_NCOLORP &&
                   NVEGF == NOAHMP_NVEGF && NVEGI == NOAHMP_NVEGI,
               "header and device layout disagree");
+
+// A few host threads that run the chunks of one parallel loop (the record packer); the calling thread takes part.
+class HostPool {
+ public:
+  explicit HostPool(int nthreads) {
+    for (int k = 1; k < nthreads; ++k) th_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    go_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size() + 1; }
+  void run(int nchunks, const std::function<void(int)>& fn) {
+    if (th_.empty() || nchunks <= 1) {
+      for (int k = 0; k < nchunks; ++k) fn(k);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      fn_ = &fn; nchunks_ = nchunks; next_.store(0); pending_ = (int)th_.size(); ++gen_;
+    }
+    go_.notify_all();
+    work();
+    std::unique_lock<std::mutex> g(mu_);
+    done_.wait(g, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void work() {
+    for (int k; (k = next_.fetch_add(1)) < nchunks_;) (*fn_)(k);
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        go_.wait(g, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      work();
+      std::lock_guard<std::mutex> g(mu_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable go_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int nchunks_ = 0, pending_ = 0;
+  std::atomic<int> next_{0};
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
 
 struct noahmp_ctx {
   int device = 0;
@@ -45,6 +116,18 @@ struct noahmp_ctx {
   int rring_slots = 0;
   cudaEvent_t* ev_slot = nullptr;  // [rring_slots]
   cudaEvent_t ev_rcopied = nullptr;
+  // zero suppression of record planes before they cross the host link (noahmp_set_record_packing)
+  unsigned pack_planes = (1u << F_SOLDN) | (1u << F_PRCP);
+  int pack_threads = 0;             // 0: default_pack_threads()
+  HostPool* pool = nullptr;
+  uint32_t* stage = nullptr;        // page-locked: per ring slot and candidate plane, occupancy | before | values
+  size_t cap_stage = 0;             // bytes
+  cudaEvent_t* ev_stage = nullptr;  // [rring_slots] the copies out of a slot's staging area have completed
+  int nev_stage = 0;
+  std::vector<uint32_t> pack_scratch;   // the packer's intermediate copy of one plane's non-zero words
+  std::vector<int> slot_sparse;     // which planes of the record a ring slot holds are packed
+  double pack_seconds = 0.0;        // wall time the calling thread has spent packing (its helpers work inside it)
+  int64_t h2d_bytes = 0;            // bytes the advance_* entry points have copied host -> device
   int64_t launches = 0;
   std::string err;
 };
@@ -82,11 +165,13 @@ int cuda_fail(noahmp_ctx* c, cudaError_t e, const char* where) {
 
 typedef void (*StepKernel)(const StepArgs);
 
-StepKernel pick_kernel(bool is_default, bool diag, bool budget) {
+StepKernel pick_kernel(bool is_default, bool diag, bool budget, bool packed = false) {
 #ifdef NMP_EXPERIMENT_ONE_KERNEL   // tuning builds only (tools/tune_builds.sh): compile just the benchmarked variant
-  (void)is_default; (void)diag; (void)budget;
+  (void)is_default; (void)diag; (void)budget; (void)packed;
   return column_step_kernel<OptDefault, false, false, false>;
 #else
+  // zero-suppressed record planes: only noahmp_advance_records_host produces them, and it launches without diagnostics
+  if (packed) return is_default ? column_step_kernel<OptDefault, false, false, true, true> : column_step_kernel<OptRuntime, true, false, true, true>;
   if (is_default) {
     if (diag) return column_step_kernel<OptDefault, false, true, true>;
     if (budget) return column_step_kernel<OptDefault, false, false, true>;
@@ -160,6 +245,90 @@ __global__ void __launch_bounds__(256) synth_forcing_kernel(int64_t ncol, int64_
   forcing[F_COSZ * ncol + i] = cosz;
 }
 
+// ---- zero suppression of one record plane (host) --------------------------------------------------------------------
+// occupancy[g] bit b = word 32 g + b of the plane is not the bit pattern 0; before[g] = non-zero words in groups < g;
+// values = the non-zero words in order.  The plane is read ONCE: chunks of groups are compacted in parallel into `scratch`
+// (each at the position of its first column), the chunk totals are summed, and a second parallel loop copies each chunk's
+// words to their final place and adds the chunk's base to its `before` words.  A sample of the plane is looked at first:
+// a plane that is clearly fuller than `max_fill` is not packed at all (the caller sends it as it is).  Returns the number
+// of non-zero words, or -1 when the plane is (or is estimated to be) more than `max_fill` non-zero.
+inline uint32_t occupancy32(const uint32_t* x) {
+#if defined(__SSE2__)
+  const __m128i z = _mm_setzero_si128();
+  uint32_t zero = 0;
+  for (int k = 0; k < 8; ++k) {
+    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(x + 4 * k));
+    zero |= (uint32_t)_mm_movemask_ps(_mm_castsi128_ps(_mm_cmpeq_epi32(v, z))) << (4 * k);
+  }
+  return ~zero;
+#else
+  uint32_t m = 0;
+  for (int b = 0; b < 32; ++b) m |= (uint32_t)(x[b] != 0u) << b;
+  return m;
+#endif
+}
+int64_t pack_plane(HostPool* pool, const float* plane, int64_t n, uint32_t* occupancy, uint32_t* before, float* values,
+                   uint32_t* scratch, double max_fill) {
+  const uint32_t* x = reinterpret_cast<const uint32_t*>(plane);
+  const int64_t G = (n + 31) >> 5, Gfull = n >> 5;
+  if (max_fill < 1.0 && n >= (1 << 16)) {   // 4096 evenly spaced words: is the plane worth reading?
+    const int64_t stride = n / 4096;
+    int64_t hit = 0;
+    for (int64_t k = 0; k < 4096; ++k) hit += x[k * stride + (k & 31)] != 0u;
+    if ((double)hit > (max_fill + 0.1) * 4096.0) return -1;
+  }
+  const int workers = pool ? pool->size() : 1;
+  int nchunks = (int)std::min<int64_t>((int64_t)workers * 4, std::max<int64_t>(1, G / 2048));
+  const int64_t per = (G + nchunks - 1) / nchunks;
+  nchunks = (int)((G + per - 1) / per);
+  std::vector<int64_t> count((size_t)nchunks + 1, 0);
+  auto compact = [&](int c) {
+    const int64_t g0 = c * per, g1 = std::min(G, g0 + per);
+    uint32_t* out = scratch + 32 * g0;
+    int64_t k = 0;
+    for (int64_t g = g0; g < g1; ++g) {
+      const uint32_t* src = x + 32 * g;
+      uint32_t m;
+      if (g < Gfull) m = occupancy32(src);
+      else {
+        m = 0;
+        for (int64_t i = 32 * g; i < n; ++i) m |= (uint32_t)(x[i] != 0u) << (i - 32 * g);
+      }
+      occupancy[g] = m;
+      before[g] = (uint32_t)k;
+      if (m == 0xffffffffu) {
+        std::memcpy(out + k, src, 128);
+        k += 32;
+      } else {
+        for (; m; m &= m - 1) out[k++] = src[__builtin_ctz(m)];
+      }
+    }
+    count[(size_t)c + 1] = k;
+  };
+  if (pool) pool->run(nchunks, compact);
+  else for (int c = 0; c < nchunks; ++c) compact(c);
+  for (int c = 0; c < nchunks; ++c) count[(size_t)c + 1] += count[(size_t)c];
+  const int64_t nnz = count[(size_t)nchunks];
+  if ((double)nnz > max_fill * (double)n) return -1;
+  auto place = [&](int c) {
+    const int64_t g0 = c * per, g1 = std::min(G, g0 + per), base = count[(size_t)c];
+    std::memcpy(reinterpret_cast<uint32_t*>(values) + base, scratch + 32 * g0, sizeof(uint32_t) * (size_t)(count[(size_t)c + 1] - base));
+    if (base)
+      for (int64_t g = g0; g < g1; ++g) before[g] += (uint32_t)base;
+  };
+  if (pool) pool->run(nchunks, place);
+  else for (int c = 0; c < nchunks; ++c) place(c);
+  return nnz;
+}
+// a plane more than this full travels dense: packing it would save less than the occupancy words and the second pass cost
+constexpr double kPackMaxFill = 0.80;
+int default_pack_threads() {
+  cpu_set_t set;
+  int allowed = (int)std::thread::hardware_concurrency();
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) allowed = CPU_COUNT(&set);
+  return std::max(1, std::min(8, allowed));
+}
+
 std::string g_init_error = "null context";   // text of the last failed noahmp_init (there is no context to hold it)
 
 int ensure(noahmp_ctx* c, void** p, size_t* cap, size_t need) {
@@ -211,6 +380,10 @@ int noahmp_finalize(noahmp_ctx* c) {
   for (int k = 0; k < c->rring_slots; ++k) cudaEventDestroy(c->ev_slot[k]);
   delete[] c->ev_slot;
   if (c->ev_rcopied) cudaEventDestroy(c->ev_rcopied);
+  for (int k = 0; k < c->nev_stage; ++k) cudaEventDestroy(c->ev_stage[k]);
+  delete[] c->ev_stage;
+  if (c->stage) cudaFreeHost(c->stage);
+  delete c->pool;
   delete c;
   return 0;
 }
@@ -265,6 +438,7 @@ int noahmp_set_tables(noahmp_ctx* c, const float* gen, int ngen, const float* so
 struct ForcingSource {
   const float* forcing = nullptr; int64_t forcing_stride = 0;
   const float* records = nullptr; int64_t record_stride = 0; const float* geo = nullptr; const noahmp_step_forcing* steps = nullptr;
+  const int* sp0 = nullptr; const int* sp1 = nullptr;   // per step: packed planes of rec0 / rec1 (null: dense records)
 };
 
 static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
@@ -294,11 +468,14 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
   a.static_i = static_i_dev; a.diag = diag_dev;
   a.records = src.records; a.record_stride = src.record_stride; a.geo = src.geo;
   std::memset(a.tab, 0, sizeof(a.tab));
+  bool packed = false;
   if (src.records)
     for (int s = 0; s < nsteps; ++s) {
       const noahmp_step_forcing& q = src.steps[s];
-      a.tab[s] = StepForcing{q.rec0, q.rec1, q.weight, q.sd, q.cd, q.ch0, q.sh0};
+      a.tab[s] = StepForcing{q.rec0, q.rec1, q.weight, q.sd, q.cd, q.ch0, q.sh0, src.sp0 ? src.sp0[s] : 0, src.sp1 ? src.sp1[s] : 0};
+      packed = packed || a.tab[s].sp0 != 0 || a.tab[s].sp1 != 0;
     }
+  if (packed && (diag_dev != nullptr || budget_dev == nullptr)) return fail(c, -1, "packed records are launched with a budget and without diagnostics");
   a.budget = budget_dev ? budget_dev : c->dev_budget_scratch;
   a.tables = c->dev_tables; a.ncol = ncol; a.nsteps = nsteps; a.final_launch = final_launch;
   a.rc.dt = rp->dt;
@@ -306,7 +483,7 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
   a.rc.zref = rp->zref; a.rc.co2_frac = rp->co2_frac; a.rc.o2_frac = rp->o2_frac; a.rc.foln = rp->foln;
   a.rc.yearlen = rp->yearlen; a.rc.julian0 = rp->julian0;
   a.opt = c->opt;
-  StepKernel k = pick_kernel(c->opt_is_default, diag_dev != nullptr, budget_dev != nullptr);
+  StepKernel k = pick_kernel(c->opt_is_default, diag_dev != nullptr, budget_dev != nullptr, packed);
   const int block = NMP_BLOCK;
   const int64_t grid = (ncol + block - 1) / block;
   if (grid > 0x7fffffffLL) return fail(c, -6, "ncol too large for one launch");
@@ -429,6 +606,7 @@ int64_t noahmp_advance_host(noahmp_ctx* c, const noahmp_run_params* rp, int64_t 
     CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
     CUDA_TRY(c, cudaMemcpyAsync(c->fbuf[b], forcing_host + (size_t)s0 * step_words, sizeof(float) * step_words * (size_t)n,
                                 cudaMemcpyHostToDevice, c->copy_stream));
+    c->h2d_bytes += (int64_t)(sizeof(float) * step_words * (size_t)n);
     CUDA_TRY(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_copied[b], 0));
     noahmp_run_params r = *rp;
@@ -466,7 +644,9 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
   // records a launch can touch: at most two per step; the ring holds two launches' worth so that the copies of launch
   // k+1 run while launch k computes (a record shared by consecutive launches is copied once)
   const int slots = 4 * g < 4 ? 4 : 4 * g;
-  const size_t rec_words = (size_t)8 * (size_t)ncol;
+  const size_t n = (size_t)ncol, G = (n + 31) >> 5;
+  const size_t host_rec_words = 8 * n;            // records_host is dense
+  const size_t rec_words = 8 * n + 16 * G;        // a ring slot: the eight planes + occupancy / before words of packed planes
   if (!c->copy_stream) {
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
@@ -496,17 +676,51 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
     c->cap_rring = need;
   }
   const int R = c->rring_slots;
+  // packing: candidate planes, their page-locked staging areas (one per ring slot), the host threads
+  int cand[8], ncand = 0;
+  for (int q = 0; q < 8; ++q)
+    if ((c->pack_planes >> q) & 1u) cand[ncand++] = q;
+  const size_t stage_words = 2 * G + n;           // occupancy | before | values of one plane
+  if (ncand) {
+    if (R > c->nev_stage) {
+      cudaEvent_t* ev = new cudaEvent_t[R];
+      for (int k = 0; k < R; ++k) {
+        if (k < c->nev_stage) ev[k] = c->ev_stage[k];
+        else CUDA_TRY(c, cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+      }
+      delete[] c->ev_stage;
+      c->ev_stage = ev;
+      c->nev_stage = R;
+    }
+    const size_t need_stage = sizeof(uint32_t) * stage_words * (size_t)ncand * (size_t)R;
+    if (need_stage > c->cap_stage) {
+      CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+      if (c->stage) cudaFreeHost(c->stage);
+      c->stage = nullptr;
+      c->cap_stage = 0;
+      CUDA_TRY(c, cudaHostAlloc((void**)&c->stage, need_stage, cudaHostAllocDefault));
+      c->cap_stage = need_stage;
+    }
+    if (c->pack_scratch.size() < 32 * G) c->pack_scratch.resize(32 * G);
+    const int want = c->pack_threads > 0 ? c->pack_threads : default_pack_threads();
+    if (!c->pool || c->pool->size() != want) {
+      delete c->pool;
+      c->pool = new HostPool(want);
+    }
+  }
   cudaStream_t cs = c->stream;
   CUDA_TRY(c, cudaMemsetAsync(c->dev_budget_scratch, 0, sizeof(double) * NBUDGET, cs));
   // nothing of an earlier call may still read the ring when the first copy lands
   for (int k = 0; k < R; ++k) CUDA_TRY(c, cudaEventRecord(c->ev_slot[k], cs));
   std::vector<int> resident((size_t)R, -1);
+  c->slot_sparse.assign((size_t)R, 0);
   noahmp_step_forcing tab[MAX_RECORD_STEPS];
+  int sp0[MAX_RECORD_STEPS], sp1[MAX_RECORD_STEPS];
   for (int s0 = 0; s0 < nsteps; s0 += g) {
-    const int n = (nsteps - s0 < g) ? nsteps - s0 : g;
+    const int nl = (nsteps - s0 < g) ? nsteps - s0 : g;
     bool copied = false;
     std::vector<int> claimed((size_t)R, -1);   // record each slot holds for THIS launch
-    for (int s = 0; s < n; ++s) {
+    for (int s = 0; s < nl; ++s) {
       const noahmp_step_forcing& q = steps[s0 + s];
       const int need_rec[2] = {q.rec0, q.weight == 0.0f ? q.rec0 : q.rec1};
       for (int k = 0; k < 2; ++k) {
@@ -515,15 +729,57 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
           return fail(c, -5, "the records of one launch must be within 4 x steps_per_launch consecutive records");
         claimed[(size_t)slot] = r;
         if (resident[(size_t)slot] == r) continue;
+        const float* hrec = records_host + (size_t)r * host_rec_words;
+        float* drec = c->rring + (size_t)slot * rec_words;
+        // pack the candidate planes of this record (host threads) while the device works on what is already queued;
+        // the staging area of the slot is free once the copies of the record it held before have completed
+        int sparse = 0;
+        int64_t nnz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (ncand) {
+          CUDA_TRY(c, cudaEventSynchronize(c->ev_stage[slot]));
+          const auto t_pack = std::chrono::steady_clock::now();
+          for (int j = 0; j < ncand; ++j) {
+            uint32_t* st = c->stage + ((size_t)slot * (size_t)ncand + (size_t)j) * stage_words;
+            nnz[cand[j]] = pack_plane(c->pool, hrec + (size_t)cand[j] * n, ncol, st, st + G, reinterpret_cast<float*>(st + 2 * G),
+                                      c->pack_scratch.data(), kPackMaxFill);
+            if (nnz[cand[j]] >= 0) sparse |= 1 << cand[j];
+          }
+          c->pack_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pack).count();
+        }
         CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_slot[slot], 0));   // last launch that read this slot
-        CUDA_TRY(c, cudaMemcpyAsync(c->rring + (size_t)slot * rec_words, records_host + (size_t)r * rec_words,
-                                    sizeof(float) * rec_words, cudaMemcpyHostToDevice, c->copy_stream));
+        for (int qa = 0; qa < 8;) {
+          if ((sparse >> qa) & 1) {
+            int j = 0;
+            while (cand[j] != qa) ++j;
+            const uint32_t* st = c->stage + ((size_t)slot * (size_t)ncand + (size_t)j) * stage_words;
+            CUDA_TRY(c, cudaMemcpyAsync(reinterpret_cast<uint32_t*>(drec + 8 * n) + (size_t)(2 * qa) * G, st, sizeof(uint32_t) * 2 * G,
+                                        cudaMemcpyHostToDevice, c->copy_stream));
+            c->h2d_bytes += (int64_t)(sizeof(uint32_t) * 2 * G);
+            if (nnz[qa] > 0) {
+              CUDA_TRY(c, cudaMemcpyAsync(drec + (size_t)qa * n, st + 2 * G, sizeof(float) * (size_t)nnz[qa], cudaMemcpyHostToDevice,
+                                          c->copy_stream));
+              c->h2d_bytes += (int64_t)(sizeof(float) * (size_t)nnz[qa]);
+            }
+            ++qa;
+          } else {   // a run of dense planes travels as one copy
+            int qb = qa + 1;
+            while (qb < 8 && !((sparse >> qb) & 1)) ++qb;
+            CUDA_TRY(c, cudaMemcpyAsync(drec + (size_t)qa * n, hrec + (size_t)qa * n, sizeof(float) * n * (size_t)(qb - qa),
+                                        cudaMemcpyHostToDevice, c->copy_stream));
+            c->h2d_bytes += (int64_t)(sizeof(float) * n * (size_t)(qb - qa));
+            qa = qb;
+          }
+        }
+        if (ncand) CUDA_TRY(c, cudaEventRecord(c->ev_stage[slot], c->copy_stream));
         resident[(size_t)slot] = r;
+        c->slot_sparse[(size_t)slot] = sparse;
         copied = true;
       }
       tab[s] = q;
       tab[s].rec0 = need_rec[0] % R;
       tab[s].rec1 = need_rec[1] % R;
+      sp0[s] = c->slot_sparse[(size_t)tab[s].rec0];
+      sp1[s] = c->slot_sparse[(size_t)tab[s].rec1];
     }
     if (copied) {
       CUDA_TRY(c, cudaEventRecord(c->ev_rcopied, c->copy_stream));
@@ -533,10 +789,11 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
     r.julian0 = rp->julian0 + (double)s0 * (double)rp->dt / 86400.0;
     ForcingSource src;
     src.records = c->rring; src.record_stride = (int64_t)rec_words; src.geo = geo_dev; src.steps = tab;
-    const int rc = run_impl(c, &r, ncol, n, state_dev, src, static_f_dev, static_i_dev, nullptr, c->dev_budget_scratch,
+    src.sp0 = sp0; src.sp1 = sp1;
+    const int rc = run_impl(c, &r, ncol, nl, state_dev, src, static_f_dev, static_i_dev, nullptr, c->dev_budget_scratch,
                             s0 + g >= nsteps ? 1 : 0);
     if (rc) return rc;
-    for (int s = 0; s < n; ++s) {   // the slots this launch reads are busy until it ends
+    for (int s = 0; s < nl; ++s) {   // the slots this launch reads are busy until it ends
       CUDA_TRY(c, cudaEventRecord(c->ev_slot[tab[s].rec0], cs));
       if (tab[s].rec1 != tab[s].rec0) CUDA_TRY(c, cudaEventRecord(c->ev_slot[tab[s].rec1], cs));
     }
@@ -620,6 +877,29 @@ const char* noahmp_forcing_plane_name(int i) { return (i >= 0 && i < NFORCING) ?
 const char* noahmp_diag_plane_name(int i) { return (i >= 0 && i < NDIAG) ? kDiagNames[i] : nullptr; }
 const char* noahmp_budget_name(int i) { return (i >= 0 && i < NBUDGET) ? kBudgetNames[i] : nullptr; }
 int64_t noahmp_launch_count(const noahmp_ctx* c) { return c ? c->launches : -1; }
+int64_t noahmp_h2d_bytes(const noahmp_ctx* c) { return c ? c->h2d_bytes : -1; }
+double noahmp_pack_seconds(const noahmp_ctx* c) { return c ? c->pack_seconds : -1.0; }
+
+int noahmp_set_record_packing(noahmp_ctx* c, unsigned plane_mask, int host_threads) {
+  if (!c) return -1;
+  if (plane_mask > 0xffu) return fail(c, -5, "a record has eight planes: plane_mask must be below 256");
+  if (host_threads > 256) return fail(c, -5, "host_threads above 256");
+  c->pack_planes = plane_mask;
+  c->pack_threads = host_threads > 0 ? host_threads : 0;
+  return 0;
+}
+
+int64_t noahmp_pack_plane(const float* plane, int64_t ncol, uint32_t* occupancy, uint32_t* before, float* values,
+                          int host_threads) {
+  if (ncol < 0 || (ncol > 0 && (!plane || !occupancy || !before || !values))) return -1;
+  if (ncol == 0) return 0;
+  std::unique_ptr<uint32_t[]> scratch(new uint32_t[(size_t)(((ncol + 31) >> 5) * 32)]);   // not initialised on purpose
+  if (host_threads > 1) {
+    HostPool pool(host_threads > 256 ? 256 : host_threads);
+    return pack_plane(&pool, plane, ncol, occupancy, before, values, scratch.get(), 1.0);
+  }
+  return pack_plane(nullptr, plane, ncol, occupancy, before, values, scratch.get(), 1.0);
+}
 
 int noahmp_kernel_info(noahmp_ctx* c, int info[4]) {
   if (!c || !info) return -1;

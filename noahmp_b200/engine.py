@@ -176,7 +176,20 @@ class NoahMP:
                                                     _fp(np.ascontiguousarray(scal4, np.float32)), _dev_ptr(out)),
                     "noahmp_prepare_forcing")
 
+    def set_record_packing(self, plane_mask: int = 0xA0, host_threads: int = 0) -> None:
+        """``noahmp_set_record_packing``: which planes of a record :meth:`advance_records_host` zero-suppresses on the host
+        before the copy (default SOLDN | PRCP; 0 = off) and with how many host threads (0 = default)."""
+        self._check(self.lib.noahmp_set_record_packing(self.ctx, int(plane_mask), int(host_threads)), "noahmp_set_record_packing")
+
     # -- introspection -----------------------------------------------------------------------------------
+    def h2d_bytes(self) -> int:
+        """Bytes the ``advance_*`` entry points of this context have copied host -> device so far."""
+        return int(self.lib.noahmp_h2d_bytes(self.ctx))
+
+    def pack_seconds(self) -> float:
+        """Wall time ``advance_records_host`` has spent zero-suppressing record planes on the host so far."""
+        return float(self.lib.noahmp_pack_seconds(self.ctx))
+
     def launch_count(self) -> int:
         return int(self.lib.noahmp_launch_count(self.ctx))
 
@@ -209,6 +222,20 @@ class NoahMP:
 
 # ---- the reference's two entry-point names (engine:5-10) ---------------------------------------------
 _default: NoahMP | None = None
+
+
+def pack_plane(plane: np.ndarray, host_threads: int = 1, fast="fast"):
+    """``noahmp_pack_plane`` (host only, no device): the zero-suppressed form of one record plane that
+    ``noahmp_advance_records_host`` sends over the host link.  Returns (occupancy uint32[G], before uint32[G],
+    values float32[nnz]) with G = ceil(ncol / 32)."""
+    plane = np.ascontiguousarray(plane, np.float32)
+    n = plane.shape[0]
+    g = (n + 31) // 32
+    occ, bef, val = np.zeros(g, np.uint32), np.zeros(g, np.uint32), np.zeros(max(n, 1), np.float32)
+    nnz = load(fast).noahmp_pack_plane(plane.ctypes.data, n, occ.ctypes.data, bef.ctypes.data, val.ctypes.data, int(host_threads))
+    if nnz < 0:
+        raise RuntimeError("noahmp_pack_plane failed")
+    return occ, bef, val[:nnz].copy()
 
 
 def noahmp_init(tables: ParamTables | None = None, opts=None, device: int = 0, fast: bool = False) -> NoahMP:

@@ -17,7 +17,7 @@ HEADER = os.path.join(ROOT, "include", "noahmp_b200.h")
 def header_symbols():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(noahmp_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(noahmp_[a-z0-9_]+)\s*\(", text)))
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))

@@ -267,3 +267,48 @@ def test_streamed_records_equal_resident_records(tables, spl):
     assert np.array_equal(bsum[snap], ref[snap])
     assert np.allclose(np.delete(bsum, snap), np.delete(ref, snap), rtol=1e-12, atol=1e-9)   # fp64 atomics: order of addition
     eng.close()
+
+
+@pytest.mark.parametrize("variant", ["fast", "strict"])
+@pytest.mark.parametrize("ncol,spl", [(33, 1), (5000, 3), (70_001, 1), (70_001, 16)])
+def test_packed_records_end_in_the_same_state(tables, variant, ncol, spl):
+    """noahmp_set_record_packing: zero-suppressed record planes (the default candidates SOLDN | PRCP, every plane as a
+    candidate, packing off) give the bit-identical state and budget - the packing is lossless - and fewer bytes cross the
+    host link.  The records include a night (SOLDN all zero), a dry record, a half-zero VV plane, -0 and a ragged last group;
+    with four model steps per record the kernel interpolates between a packed and a dense plane."""
+    w, recs, geo, plan, j0, ylen = _records_case(ncol, nrec=7)
+    rng = np.random.default_rng(5)
+    recs = recs.copy()
+    recs[1, 5] = 0.0                                   # night
+    recs[2, 5, : ncol // 2] = 0.0                      # terminator
+    recs[3, 7] = 0.0                                   # dry everywhere
+    recs[4, 7, rng.random(ncol) < 0.5] = 0.0
+    recs[:, 3, rng.random(ncol) < 0.5] = 0.0           # calm meridional wind on half of the columns (packed only with mask 0xFF)
+    recs[5, 7, 0] = -0.0
+    eng = NoahMP(tables, w.opts, device=0, fast=variant)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    dgeo, sf, si = d(geo), d(w.static_f), d(w.static_i)
+    rp = eng.run_params(w.dt, synth.ZSOIL, j0, ylen)
+    steps = eng.step_table([p[0] for p in plan], [p[1] for p in plan], [p[2] for p in plan], [p[3] for p in plan])
+    hrec = torch.from_numpy(recs).pin_memory()
+    out = {}
+    for name, mask, threads in (("off", 0, 0), ("default", 0xA0, 3), ("all", 0xFF, 2)):
+        eng.set_record_packing(mask, threads)
+        st = d(w.state)
+        hb = torch.zeros(L.NBUDGET, dtype=torch.float64).pin_memory()
+        before = eng.h2d_bytes()
+        for _ in range(2):      # the second call re-uses ring and staging areas
+            st.copy_(d(w.state))
+            nflag = eng.advance_records_host(rp, st, hrec, steps, dgeo, sf, si, hb, spl)
+        out[name] = (st.cpu().numpy().view(np.int32), hb.numpy().copy(), nflag, (eng.h2d_bytes() - before) // 2)
+    for name in ("default", "all"):
+        assert np.array_equal(out[name][0], out["off"][0]), name
+        assert out[name][2] == out["off"][2]
+        snap = [L.B["NCELL"], L.B["SNEQV"], L.B["SOILWATER"]]
+        assert np.array_equal(out[name][1][snap], out["off"][1][snap])
+        assert np.allclose(out[name][1], out["off"][1], rtol=1e-12, atol=1e-9)
+    assert out["off"][3] == 7 * 8 * 4 * ncol                        # every record once, eight dense planes
+    assert out["all"][3] < out["default"][3] < out["off"][3]
+    with pytest.raises(Exception):
+        eng.set_record_packing(0x100, 0)
+    eng.close()
