@@ -141,7 +141,9 @@ int noahmp_run_records(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t nco
 /* Streaming variant (the time-marching driver's call): state, static and geo planes stay on the device, the records
  * arrive from the host.  records_host is [nrec][8][ncol] (page-locked for the copies to overlap); steps[nsteps] index
  * into it.  Every record is copied H2D ONCE, on a private copy stream into a ring of device slots, while earlier
- * launches compute (`steps_per_launch` model steps per launch, 1..NOAHMP_MAX_RECORD_STEPS).  Returns like
+ * launches compute (`steps_per_launch` model steps per launch, 1..NOAHMP_MAX_RECORD_STEPS).  The ring holds up to 24
+ * records (a day of hourly ones; never less than 4 x steps_per_launch, never more than a quarter of the free device
+ * memory), so that the copies can run ahead of the kernel through the expensive hours of the day.  Returns like
  * noahmp_advance_host. */
 int64_t noahmp_advance_records_host(noahmp_ctx* ctx, const noahmp_run_params* rp, int64_t ncol, int nsteps,
                                     float* state_dev, const float* records_host, int nrec,

@@ -32,7 +32,7 @@ struct StepArgs {
   const float* static_f;  // [NSTATIC_F][ncol]
   const int* static_i;    // [ncol]
   float* diag;            // [NDIAG][ncol] or null
-  double* budget;         // [NBUDGET] or null
+  double* budget;         // [NBUDGET_REP][NBUDGET] copies, all zero before the launch (budget_combine_kernel), or null
   const Tables* tables;   // global copy, staged to shared memory
   int64_t ncol;
   int nsteps;
@@ -79,6 +79,79 @@ __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
   return v;
+}
+
+constexpr int NBUDGET_REP = 64;   // copies of the budget vector the CTAs add into (one 128-byte line each)
+
+// Folds the copies into the caller's vector (which accumulates over launches) and clears them for the next launch.
+__global__ void budget_combine_kernel(double* __restrict__ rep, double* __restrict__ dst) {
+  const int q = threadIdx.x;
+  if (q >= NBUDGET) return;
+  double r = 0.0;
+  for (int k = 0; k < NBUDGET_REP; ++k) {
+    const double x = rep[k * NBUDGET + q];
+    r = (q == B_ERRWAT_MAXABS) ? fmax(r, x) : r + x;
+    rep[k * NBUDGET + q] = 0.0;
+  }
+  dst[q] = (q == B_ERRWAT_MAXABS) ? fmax(dst[q], r) : dst[q] + r;
+}
+
+// Sums of up to 16 per-lane doubles over the warp, all at once: at every level of the butterfly a lane keeps half of the
+// values it holds and hands the other half to its partner, so 8 + 4 + 2 + 1 + 1 exchanges do what 16 x 5 would (the
+// shuffle pipe moves one warp-instruction per clock per SM: the plain form cost the budget builds 12 % of the step).
+// Lane l returns the total of value l >> 1.
+template <int N>
+__device__ __forceinline__ double warp_sums(const double (&v)[N]) {
+  static_assert(N <= 16, "one value per lane pair");
+  const unsigned lane = threadIdx.x & 31u;
+  double a8[8], a4[4], a2[2];
+  static_for<0, 7>([&](auto j_) { constexpr int j = decltype(j_)::value;
+    const double lo = (j < N) ? v[j < N ? j : 0] : 0.0, hi = (j + 8 < N) ? v[j + 8 < N ? j + 8 : 0] : 0.0;
+    const bool up = (lane & 16u) != 0;
+    a8[j] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, 16);
+  });
+  static_for<0, 3>([&](auto j_) { constexpr int j = decltype(j_)::value;
+    const bool up = (lane & 8u) != 0;
+    a4[j] = (up ? a8[j + 4] : a8[j]) + __shfl_xor_sync(0xffffffffu, up ? a8[j] : a8[j + 4], 8);
+  });
+  static_for<0, 1>([&](auto j_) { constexpr int j = decltype(j_)::value;
+    const bool up = (lane & 4u) != 0;
+    a2[j] = (up ? a4[j + 2] : a4[j]) + __shfl_xor_sync(0xffffffffu, up ? a4[j] : a4[j + 2], 4);
+  });
+  const bool up = (lane & 2u) != 0;
+  double r = (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+// N budget slots starting at Q0, summed (B_ERRWAT_MAXABS: maximum) over the CTA: the warp (warp_sums), the warps through
+// shared memory, then ONE atomic per CTA and slot into one of NBUDGET_REP copies of the vector.  Called by every thread of
+// the CTA at the same place; consecutive calls alternate between two buffers (a warp may write the next call's partial
+// sums while another still reads this call's: the barrier of the call in between orders the re-use).
+constexpr int NBUDGET_STEP = B_RUNOFF_DT - B_ERRWAT_SUM + 1;   // the slots that sum over the steps
+template <int Q0, int N>
+__device__ __forceinline__ void budget_reduce(double* budget, double (*red)[NMP_BLOCK / 32], const double (&v)[N]) {
+  constexpr int JMAX = B_ERRWAT_MAXABS - Q0;   // the slot that takes the maximum, if it is among these
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const double r = warp_sums<N>(v);            // (the maximum slot's sum is computed too and not used)
+  if ((lane & 1u) == 0 && (lane >> 1) < (unsigned)N && (int)(lane >> 1) != JMAX) red[lane >> 1][warp] = r;
+  if (JMAX >= 0 && JMAX < N) {
+    const double m = warp_max(v[JMAX >= 0 && JMAX < N ? JMAX : 0]);
+    if (lane == 0) red[JMAX >= 0 && JMAX < N ? JMAX : 0][warp] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    const int j = threadIdx.x, q = Q0 + j, nw = (int)(blockDim.x >> 5);
+    double t = red[j][0];
+    if (q == B_ERRWAT_MAXABS) {
+      for (int k = 1; k < nw; ++k) t = fmax(t, red[j][k]);
+    } else {
+      for (int k = 1; k < nw; ++k) t += red[j][k];
+    }
+    double* dst = budget + (size_t)(blockIdx.x & (NBUDGET_REP - 1)) * NBUDGET + q;
+    if (q == B_ERRWAT_MAXABS) atomicMax(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double_as_longlong(t));
+    else atomicAdd(dst, t);
+  }
 }
 
 template <class Opt, bool EXT, bool DIAG, bool BUDGET, bool PACKED = false>
@@ -151,8 +224,8 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
   if (DIAG && dg.base != nullptr) {
     static_for<0, 5>([&](auto q_) { constexpr int q = decltype(q_)::value; acc[q] = dg.base[(int64_t)(D_ACCPRCP + q) * n]; });
   }
-  double b_errwat = 0.0, b_errabs = 0.0, b_errmax = 0.0, b_fsa = 0.0, b_fsr = 0.0, b_fira = 0.0, b_fsh = 0.0, b_lh = 0.0;
-  double b_ssoil = 0.0, b_prcp = 0.0, b_et = 0.0, b_runoff = 0.0;
+  // budget sums: reduced over the CTA at the end of EVERY step (budget_reduce) - no fp64 accumulator lives across the step
+  __shared__ double red[BUDGET ? 2 : 1][BUDGET ? NBUDGET_STEP : 1][BUDGET ? NMP_BLOCK / 32 : 1];
 
 #pragma unroll 1
   for (int s = 0; s < a.nsteps; ++s) {
@@ -359,11 +432,15 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
       acc[0] = acc[0] + f.PRCP * DT; acc[1] = acc[1] + w.ECAN * DT; acc[2] = acc[2] + w.ETRAN * DT;
       acc[3] = acc[3] + EDIR * DT; acc[4] = acc[4] + w.runsrf * DT; acc[5] = acc[5] + w.runsub * DT;
     }
-    if (BUDGET) {
-      b_errwat += (double)ERRWAT; b_errabs += fabs((double)ERRWAT); b_errmax = fmax(b_errmax, fabs((double)ERRWAT));
-      b_fsa += (double)e.FSA; b_fsr += (double)e.FSR; b_fira += (double)e.FIRA; b_fsh += (double)e.FSH;
-      b_lh += (double)(e.FCEV + e.FGEV + e.FCTR); b_ssoil += (double)e.SSOIL; b_prcp += (double)(f.PRCP * DT);
-      b_et += (double)((w.ECAN + w.ETRAN + EDIR) * DT); b_runoff += (double)((w.runsrf + w.runsub) * DT);
+    if constexpr (BUDGET) {
+      // selects, not products: a flagged column's values may be NaN/Inf (0 x NaN = NaN would poison the domain sums)
+      const bool on = active && !badtype;
+      auto keep = [&](float x) { return (on && isfinite(x)) ? (double)x : 0.0; };
+      double v[NBUDGET_STEP];   // slots B_ERRWAT_SUM .. B_RUNOFF_DT
+      v[0] = keep(ERRWAT); v[1] = keep(fabsf(ERRWAT)); v[2] = v[1]; v[3] = keep(e.FSA); v[4] = keep(e.FSR); v[5] = keep(e.FIRA);
+      v[6] = keep(e.FSH); v[7] = keep(e.FCEV + e.FGEV + e.FCTR); v[8] = keep(e.SSOIL); v[9] = keep(f.PRCP * DT);
+      v[10] = keep((w.ECAN + w.ETRAN + EDIR) * DT); v[11] = keep((w.runsrf + w.runsub) * DT);
+      budget_reduce<B_ERRWAT_SUM, NBUDGET_STEP>(a.budget, red[s & 1], v);
     }
   }
 
@@ -391,9 +468,8 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
     }
   }
 
-  // ---- budget reduction: warp shuffle, one atomic per warp and quantity --------------------------------
-  if (BUDGET) {
-    // selects, not products: a flagged column's accumulators may be NaN/Inf (0 x NaN = NaN would poison the domain sums)
+  // ---- end-of-launch budget slots: cells, flagged columns, snow and soil water of the final state -------------------
+  if constexpr (BUDGET) {
     const bool on = active && !badtype;
     const bool fin = active && a.final_launch;
     auto keep = [&](double x) { return (on && isfinite(x)) ? x : 0.0; };
@@ -402,22 +478,11 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
       const float thick = (k == 1) ? -rc.zsoil[0] : (rc.zsoil[k > 1 ? k - 2 : 0] - rc.zsoil[k - 1]);
       soilw += (double)(c.SMC[IX4(k)] * thick * 1000.0f);
     });
-    double v[NBUDGET];
-    v[B_NCELL] = (fin && on) ? 1.0 : 0.0; v[B_NFLAGGED] = (active && anyflag != 0) ? 1.0 : 0.0; v[B_ERRWAT_SUM] = keep(b_errwat);
-    v[B_ERRWAT_ABS] = keep(b_errabs); v[B_ERRWAT_MAXABS] = keep(b_errmax); v[B_FSA] = keep(b_fsa); v[B_FSR] = keep(b_fsr);
-    v[B_FIRA] = keep(b_fira); v[B_FSH] = keep(b_fsh); v[B_LH] = keep(b_lh); v[B_SSOIL] = keep(b_ssoil);
-    v[B_PRCP_DT] = keep(b_prcp); v[B_ET_DT] = keep(b_et); v[B_RUNOFF_DT] = keep(b_runoff);
-    v[B_SNEQV] = fin ? keep((double)c.sneqv) : 0.0; v[B_SOILWATER] = fin ? keep(soilw) : 0.0;
-    static_for<0, (NBUDGET) - 1>([&](auto q_) { constexpr int q = decltype(q_)::value;
-      const double r = (q == B_ERRWAT_MAXABS) ? warp_max(v[q]) : warp_sum(v[q]);
-      if ((threadIdx.x & 31) == 0) {
-        if (q == B_ERRWAT_MAXABS) {
-          atomicMax(reinterpret_cast<unsigned long long*>(a.budget + q), (unsigned long long)__double_as_longlong(r));
-        } else {
-          atomicAdd(a.budget + q, r);
-        }
-      }
-    });
+    double v2[2], v14[2];
+    v2[0] = (fin && on) ? 1.0 : 0.0; v2[1] = (active && anyflag != 0) ? 1.0 : 0.0;
+    v14[0] = fin ? keep((double)c.sneqv) : 0.0; v14[1] = fin ? keep(soilw) : 0.0;
+    budget_reduce<B_NCELL, 2>(a.budget, red[a.nsteps & 1], v2);
+    budget_reduce<B_SNEQV, 2>(a.budget, red[(a.nsteps + 1) & 1], v14);
   }
 }
 

@@ -101,6 +101,7 @@ struct noahmp_ctx {
   Tables host_tables{};
   Tables* dev_tables = nullptr;
   double* dev_budget_scratch = nullptr;   // NBUDGET doubles
+  double* dev_budget_rep = nullptr;       // NBUDGET_REP x NBUDGET: what the CTAs of a launch add into (column_step.cuh), zero between launches
   // grow-only DEVICE staging buffers of noahmp_run_host
   float* d_state = nullptr; float* d_forcing = nullptr; float* d_static_f = nullptr; int* d_static_i = nullptr;
   float* d_diag = nullptr;
@@ -120,10 +121,10 @@ struct noahmp_ctx {
   unsigned pack_planes = (1u << F_SOLDN) | (1u << F_PRCP);
   int pack_threads = 0;             // 0: default_pack_threads()
   HostPool* pool = nullptr;
-  uint32_t* stage = nullptr;        // page-locked: per ring slot and candidate plane, occupancy | before | values
+  uint32_t* stage = nullptr;        // page-locked: per staging area and candidate plane, occupancy | before | values
   size_t cap_stage = 0;             // bytes
-  cudaEvent_t* ev_stage = nullptr;  // [rring_slots] the copies out of a slot's staging area have completed
-  int nev_stage = 0;
+  cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // the copies out of a staging area have completed
+  unsigned stage_next = 0;          // staging areas are used in turn
   std::vector<uint32_t> pack_scratch;   // the packer's intermediate copy of one plane's non-zero words
   std::vector<int> slot_sparse;     // which planes of the record a ring slot holds are packed
   double pack_seconds = 0.0;        // wall time the calling thread has spent packing (its helpers work inside it)
@@ -322,6 +323,7 @@ int64_t pack_plane(HostPool* pool, const float* plane, int64_t n, uint32_t* occu
 }
 // a plane more than this full travels dense: packing it would save less than the occupancy words and the second pass cost
 constexpr double kPackMaxFill = 0.80;
+constexpr int kStageAreas = 4;     // page-locked staging areas of the packer (noahmp_ctx::ev_stage)
 int default_pack_threads() {
   cpu_set_t set;
   int allowed = (int)std::thread::hardware_concurrency();
@@ -353,10 +355,14 @@ int noahmp_init(noahmp_ctx** out, int device) {
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaMalloc(&c->dev_tables, sizeof(Tables));
   if (e == cudaSuccess) e = cudaMalloc(&c->dev_budget_scratch, sizeof(double) * NBUDGET);
+  if (e == cudaSuccess) e = cudaMalloc(&c->dev_budget_rep, sizeof(double) * NBUDGET * NBUDGET_REP);
+  if (e == cudaSuccess) e = cudaMemset(c->dev_budget_rep, 0, sizeof(double) * NBUDGET * NBUDGET_REP);
   if (e != cudaSuccess) {   // no context to carry the text: noahmp_last_error(NULL) returns it
     g_init_error = std::string("noahmp_init(device ") + std::to_string(device) + "): " + cudaGetErrorString(e);
     cudaGetLastError();
     if (c->dev_tables) cudaFree(c->dev_tables);
+    if (c->dev_budget_scratch) cudaFree(c->dev_budget_scratch);
+    if (c->dev_budget_rep) cudaFree(c->dev_budget_rep);
     delete c;
     return -100 - (int)e;
   }
@@ -369,6 +375,7 @@ int noahmp_finalize(noahmp_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->dev_tables);
   cudaFree(c->dev_budget_scratch);
+  cudaFree(c->dev_budget_rep);
   cudaFree(c->d_state); cudaFree(c->d_forcing); cudaFree(c->d_static_f); cudaFree(c->d_static_i); cudaFree(c->d_diag);
   cudaFree(c->fbuf[0]); cudaFree(c->fbuf[1]);
   for (int k = 0; k < 2; ++k) {
@@ -380,8 +387,8 @@ int noahmp_finalize(noahmp_ctx* c) {
   for (int k = 0; k < c->rring_slots; ++k) cudaEventDestroy(c->ev_slot[k]);
   delete[] c->ev_slot;
   if (c->ev_rcopied) cudaEventDestroy(c->ev_rcopied);
-  for (int k = 0; k < c->nev_stage; ++k) cudaEventDestroy(c->ev_stage[k]);
-  delete[] c->ev_stage;
+  for (int k = 0; k < 4; ++k)
+    if (c->ev_stage[k]) cudaEventDestroy(c->ev_stage[k]);
   if (c->stage) cudaFreeHost(c->stage);
   delete c->pool;
   delete c;
@@ -476,7 +483,9 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
       packed = packed || a.tab[s].sp0 != 0 || a.tab[s].sp1 != 0;
     }
   if (packed && (diag_dev != nullptr || budget_dev == nullptr)) return fail(c, -1, "packed records are launched with a budget and without diagnostics");
-  a.budget = budget_dev ? budget_dev : c->dev_budget_scratch;
+  // every instantiation with diagnostics also sums the budget: a launch with diag_dev but without budget_dev folds into the scratch vector
+  const bool sums = budget_dev != nullptr || diag_dev != nullptr;
+  a.budget = sums ? c->dev_budget_rep : nullptr;
   a.tables = c->dev_tables; a.ncol = ncol; a.nsteps = nsteps; a.final_launch = final_launch;
   a.rc.dt = rp->dt;
   for (int k = 0; k < 4; ++k) a.rc.zsoil[k] = rp->zsoil[k];
@@ -490,6 +499,10 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
   k<<<(unsigned)grid, block, 0, c->stream>>>(a);
   c->launches += 1;
   CUDA_TRY(c, cudaGetLastError());
+  if (sums) {
+    budget_combine_kernel<<<1, 32, 0, c->stream>>>(c->dev_budget_rep, budget_dev ? budget_dev : c->dev_budget_scratch);
+    CUDA_TRY(c, cudaGetLastError());
+  }
   return 0;
 }
 
@@ -643,10 +656,25 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
   if (g > MAX_RECORD_STEPS) g = MAX_RECORD_STEPS;
   // records a launch can touch: at most two per step; the ring holds two launches' worth so that the copies of launch
   // k+1 run while launch k computes (a record shared by consecutive launches is copied once)
-  const int slots = 4 * g < 4 ? 4 : 4 * g;
   const size_t n = (size_t)ncol, G = (n + 31) >> 5;
   const size_t host_rec_words = 8 * n;            // records_host is dense
   const size_t rec_words = 8 * n + 16 * G;        // a ring slot: the eight planes + occupancy / before words of packed planes
+  // Ring depth.  A launch needs at most 2 g records, so 4 g slots keep the copies one launch ahead.  A deeper ring lets them
+  // run further ahead: the cost of a model step varies over the day (at night there is no radiation and no photosynthesis to
+  // solve), so a run alternates between stretches bound by the link and stretches bound by the kernel, and only copies
+  // that were free to run ahead during the latter make up for the former.  Up to a day of hourly records (24), within a
+  // quarter of the free device memory.
+  int slots = 4 * g < 4 ? 4 : 4 * g;
+  {
+    int deep = nrec < 24 ? nrec : 24;
+    if (deep > slots && deep > c->rring_slots) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+      free_b += c->cap_rring;   // the present ring is given back before the deeper one is allocated
+      while (deep > slots && sizeof(float) * rec_words * (size_t)deep > free_b / 4) --deep;
+    }
+    if (deep > slots) slots = deep;
+  }
   if (!c->copy_stream) {
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
@@ -676,23 +704,15 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
     c->cap_rring = need;
   }
   const int R = c->rring_slots;
-  // packing: candidate planes, their page-locked staging areas (one per ring slot), the host threads
+  // packing: candidate planes, the page-locked staging areas (kStageAreas, used in turn), the host threads
   int cand[8], ncand = 0;
   for (int q = 0; q < 8; ++q)
     if ((c->pack_planes >> q) & 1u) cand[ncand++] = q;
   const size_t stage_words = 2 * G + n;           // occupancy | before | values of one plane
   if (ncand) {
-    if (R > c->nev_stage) {
-      cudaEvent_t* ev = new cudaEvent_t[R];
-      for (int k = 0; k < R; ++k) {
-        if (k < c->nev_stage) ev[k] = c->ev_stage[k];
-        else CUDA_TRY(c, cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-      }
-      delete[] c->ev_stage;
-      c->ev_stage = ev;
-      c->nev_stage = R;
-    }
-    const size_t need_stage = sizeof(uint32_t) * stage_words * (size_t)ncand * (size_t)R;
+    for (int k = 0; k < kStageAreas; ++k)
+      if (!c->ev_stage[k]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming));
+    const size_t need_stage = sizeof(uint32_t) * stage_words * (size_t)ncand * (size_t)kStageAreas;
     if (need_stage > c->cap_stage) {
       CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
       if (c->stage) cudaFreeHost(c->stage);
@@ -735,11 +755,13 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
         // the staging area of the slot is free once the copies of the record it held before have completed
         int sparse = 0;
         int64_t nnz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int area = (int)(c->stage_next % (unsigned)kStageAreas);   // copies leave in order: a few areas in turn suffice
         if (ncand) {
-          CUDA_TRY(c, cudaEventSynchronize(c->ev_stage[slot]));
+          c->stage_next += 1;
+          CUDA_TRY(c, cudaEventSynchronize(c->ev_stage[area]));
           const auto t_pack = std::chrono::steady_clock::now();
           for (int j = 0; j < ncand; ++j) {
-            uint32_t* st = c->stage + ((size_t)slot * (size_t)ncand + (size_t)j) * stage_words;
+            uint32_t* st = c->stage + ((size_t)area * (size_t)ncand + (size_t)j) * stage_words;
             nnz[cand[j]] = pack_plane(c->pool, hrec + (size_t)cand[j] * n, ncol, st, st + G, reinterpret_cast<float*>(st + 2 * G),
                                       c->pack_scratch.data(), kPackMaxFill);
             if (nnz[cand[j]] >= 0) sparse |= 1 << cand[j];
@@ -751,7 +773,7 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
           if ((sparse >> qa) & 1) {
             int j = 0;
             while (cand[j] != qa) ++j;
-            const uint32_t* st = c->stage + ((size_t)slot * (size_t)ncand + (size_t)j) * stage_words;
+            const uint32_t* st = c->stage + ((size_t)area * (size_t)ncand + (size_t)j) * stage_words;
             CUDA_TRY(c, cudaMemcpyAsync(reinterpret_cast<uint32_t*>(drec + 8 * n) + (size_t)(2 * qa) * G, st, sizeof(uint32_t) * 2 * G,
                                         cudaMemcpyHostToDevice, c->copy_stream));
             c->h2d_bytes += (int64_t)(sizeof(uint32_t) * 2 * G);
@@ -770,7 +792,7 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
             qa = qb;
           }
         }
-        if (ncand) CUDA_TRY(c, cudaEventRecord(c->ev_stage[slot], c->copy_stream));
+        if (ncand) CUDA_TRY(c, cudaEventRecord(c->ev_stage[area], c->copy_stream));
         resident[(size_t)slot] = r;
         c->slot_sparse[(size_t)slot] = sparse;
         copied = true;

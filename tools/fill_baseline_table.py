@@ -21,11 +21,17 @@ def sci(x):
     return "—" if x is None else f"{x:.3g}".replace("e+0", "e").replace("e+", "e")
 
 
+def bpc(x) -> float:
+    """Bytes that crossed the host link per cell-step of the e2e leg (counted by the library; 32 for dense records)."""
+    c = x["config"]
+    return x["e2e"]["h2d_bytes_per_step"] / (c["columns"] * c["model_steps_per_step"])
+
+
 def scaling_table(by_n) -> str:
     """Section 6: device-timed and end-to-end scaling beside the measured host link."""
     one = by_n[1]
     out = ["| GPUs (which) | device-timed cell-steps/s | scaling | e2e cell-steps/s (partition) | e2e scaling | e2e, equal blocks | host link while all ranks copy, GB/s: "
-           "slowest rank x N / sum of the ranks' own rates | e2e x 32 B, GB/s |", "|---|---|---|---|---|---|---|---|"]
+           "slowest rank x N / sum of the ranks' own rates | bytes over the host link per cell-step (records) | link traffic of e2e, GB/s |", "|---|---|---|---|---|---|---|---|---|"]
     for n in sorted(by_n):
         x = by_n[n]
         e, h = x["e2e"], x["e2e"]["host_link"]
@@ -35,7 +41,8 @@ def scaling_table(by_n) -> str:
         rates = h.get("h2d_gbs_sum_while_all_copy")
         out.append(f"| {n} ({', '.join(map(str, g))}) | {sci(x['value'])} | {x['value'] / one['value']:.2f}x | {sci(e['value'])} ({part}) | "
                    f"{e['value'] / one['e2e']['value']:.2f}x | {sci(eq) if eq else 'same'} | {h['h2d_gbs_all_gpus']:.0f} / "
-                   f"{(f'{rates:.0f}' if rates else 'n/a')} | {e['value'] * 32 / 1e9:.0f} |")
+                   f"{(f'{rates:.0f}' if rates else 'n/a')} | {bpc(x):.1f} ({'packed' if 'zero-suppressed' in e.get('records', '') else 'dense'}) | "
+                   f"{e['value'] * bpc(x) / 1e9:.0f} |")
     return "\n".join(out)
 
 
