@@ -39,8 +39,11 @@ def scaling_table(by_n) -> str:
         eq = (e.get("equal_blocks") or {}).get("value")
         part = "link-weighted" if eq else "equal"
         rates = h.get("h2d_gbs_sum_while_all_copy")
+        packed = "zero-suppressed" in e.get("records", "")
+        # like with like: a line with dense records is set against the one-GPU line's dense-records leg
+        base = one["e2e"]["value"] if packed or "dense_records" not in one["e2e"] else one["e2e"]["dense_records"]["value"]
         out.append(f"| {n} ({', '.join(map(str, g))}) | {sci(x['value'])} | {x['value'] / one['value']:.2f}x | {sci(e['value'])} ({part}) | "
-                   f"{e['value'] / one['e2e']['value']:.2f}x | {sci(eq) if eq else 'same'} | {h['h2d_gbs_all_gpus']:.0f} / "
+                   f"{e['value'] / base:.2f}x{'' if packed or n == 1 else ' of the dense one-GPU leg'} | {sci(eq) if eq else 'same'} | {h['h2d_gbs_all_gpus']:.0f} / "
                    f"{(f'{rates:.0f}' if rates else 'n/a')} | {bpc(x):.1f} ({'packed' if 'zero-suppressed' in e.get('records', '') else 'dense'}) | "
                    f"{e['value'] * bpc(x) / 1e9:.0f} |")
     return "\n".join(out)
