@@ -71,3 +71,40 @@ def test_contiguous_day_night_plane():
     occ, before, values = pack_plane(plane, 4)
     assert values.shape[0] == 80_002 and np.array_equal(values, plane[70_001:150_003])
     assert np.array_equal(numpy_unpack(occ, before, values, n), plane)
+
+
+def test_packer_property_random_shapes():
+    """Any size, any fill pattern (runs of zeros and non-zeros of random length, as a terminator or a rain band makes them), any
+    thread count: the packed form is the stated one and unpacks to the plane bit for bit."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 20_000), seed=st.integers(0, 2**31 - 1), threads=st.integers(1, 6), mean_run=st.integers(1, 400))
+    def check(n, seed, threads, mean_run):
+        rng = np.random.default_rng(seed)
+        plane = rng.standard_normal(n).astype(np.float32)
+        pos, zero = 0, bool(rng.integers(2))
+        while pos < n:                                   # alternating runs
+            run = int(rng.geometric(1.0 / mean_run))
+            if zero:
+                plane[pos:pos + run] = 0.0
+            pos, zero = pos + run, not zero
+        occ, before, values = pack_plane(plane, threads)
+        rocc, rbefore, rvalues = numpy_pack(plane)
+        assert np.array_equal(occ, rocc) and np.array_equal(before, rbefore)
+        assert np.array_equal(values.view(np.uint32), rvalues.view(np.uint32))
+        assert np.array_equal(numpy_unpack(occ, before, values, n).view(np.uint32), plane.view(np.uint32))
+
+    check()
+
+
+def test_packer_many_threads_many_calls():
+    """The thread pool of the packer: more threads than chunks, repeated calls, a large plane split into many chunks."""
+    rng = np.random.default_rng(3)
+    plane = rng.standard_normal(3_000_001).astype(np.float32)
+    plane[rng.random(plane.shape[0]) < 0.9] = 0.0
+    ref = numpy_pack(plane)
+    for threads in (2, 7, 16, 64):
+        for _ in range(3):
+            occ, before, values = pack_plane(plane, threads)
+            assert np.array_equal(occ, ref[0]) and np.array_equal(before, ref[1]) and np.array_equal(values, ref[2])
