@@ -717,7 +717,7 @@ def run_ours(args):
             return float(t_.item()), int(eng.launch_count() - l0_), int(flagged_), same_, int(nb_.item())
 
         # The records cross the host link either as they are (eight dense planes) or with the planes that are zero over much of
-        # the grid (night-time SOLDN, dry PRCP) zero-suppressed by host threads - lossless, a small kernel on the copy stream expands the packed
+        # the grid (night-time SOLDN, dry PRCP) zero-suppressed by host threads - lossless, the kernel's load reads the packed
         # form.  Both legs run; the faster one is the headline (packing costs host memory bandwidth, which a box may not have
         # to spare when many ranks share it), the other stays beside it.
         PACK = 0xA0

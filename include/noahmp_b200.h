@@ -153,8 +153,8 @@ int64_t noahmp_advance_records_host(noahmp_ctx* ctx, const noahmp_run_params* rp
 /* Zero suppression of record planes on their way through noahmp_advance_records_host.  Short-wave radiation is zero
  * wherever it is night and precipitation wherever it is dry: before a record crosses the host link, host threads pack
  * the candidate planes (bit q of plane_mask = plane q of a record; default SOLDN | PRCP = 0xA0, 0 = off) into a 32-column
- * occupancy word + running count per group and the non-zero words themselves, and a small kernel on the copy stream
- * expands that form into the plane the step kernel reads.  Lossless and bit-identical: only the bit pattern 0 is suppressed, a plane that is more than 80 %
+ * occupancy word + running count per group and the non-zero words themselves, and the step kernel's forcing load reads
+ * that form directly.  Lossless and bit-identical: only the bit pattern 0 is suppressed, a plane that is more than 80 %
  * non-zero travels as it is.  host_threads <= 0: as many as the calling thread may run on, at most 8.  The reference has
  * no counterpart (it has no forcing ingest at all; offline/noahmp_config.py:81-82 only names the record cadence). */
 int noahmp_set_record_packing(noahmp_ctx* ctx, unsigned plane_mask, int host_threads);

@@ -17,6 +17,7 @@ struct StepForcing {
   int rec0, rec1;           // the two bracketing records (slots of the record buffer)
   float w;                  // weight of rec1 (0: rec1 is not read)
   float sd, cd, ch0, sh0;   // solar scalars of the step
+  int sp0, sp1;             // bit q set: plane q of rec0 / rec1 is zero-suppressed (ld_record); 0 for dense records
 };
 constexpr int MAX_RECORD_STEPS = 32;   // steps of one records-driven launch (the table travels as kernel parameters)
 
@@ -24,7 +25,7 @@ struct StepArgs {
   float* state;           // [NSTATE][ncol]
   const float* forcing;   // step s at forcing + s*forcing_stride, [NFORCING][ncol]; null in records mode
   int64_t forcing_stride;
-  const float* records;   // records mode: record r at records + r*record_stride, [8][ncol]
+  const float* records;   // records mode: record r at records + r*record_stride, [8][ncol] (+ [8][2][ceil(ncol/32)] words when packed)
   int64_t record_stride;
   const float* geo;       // records mode: [4][ncol] sin(lat) cos(lat) sin(lon) cos(lon)
   StepForcing tab[MAX_RECORD_STEPS];
@@ -51,19 +52,22 @@ __device__ __forceinline__ float ld_forcing(const float* p) {
 #endif
 }
 
-// A record plane that crossed the host link zero-suppressed (noahmp_advance_records_host packs the planes that are zero over
-// much of the grid - night-time SOLDN, dry PRCP - csrc/noahmp_abi.cu: pack_plane) is expanded here, on the copy stream, into
-// the plane the step kernel reads: `packed` = one occupancy word per 32 columns, then per group the number of non-zero
-// words before it, then the non-zero words in order.  Lossless: a stored word is written as it is, a suppressed one is +0
-// (the packer suppresses the bit pattern 0 only, so -0 travels).  One streaming pass, HBM-bound.
-__global__ void __launch_bounds__(256) unpack_plane_kernel(const uint32_t* __restrict__ packed, int64_t n, float* __restrict__ plane) {
+// One plane of a forcing record.  Dense: element ii of plane q.  Zero-suppressed (noahmp_advance_records_host packs the
+// planes that are zero over much of the grid - night-time SOLDN, dry PRCP - before they cross the host link): behind the
+// eight planes the record carries, per plane, a 32-column occupancy word and the number of non-zero words before that
+// group; the non-zero words themselves lie compacted at the start of the plane.  Lossless: a stored word is returned as it
+// is, a suppressed one is +0 (the packer suppresses the bit pattern 0 only, so -0 travels).
+// PACKED is a template parameter of the kernel so that launches on dense records run the code they always ran.
+template <bool PACKED>
+__device__ __forceinline__ float ld_record(const float* rec, int q, int sparse, int64_t n, int64_t ii) {
+  if (!PACKED || !((sparse >> q) & 1)) return ld_forcing(rec + q * n + ii);
   const int64_t G = (n + 31) >> 5;
-  const float* values = reinterpret_cast<const float*>(packed + 2 * G);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t m = __ldg(packed + (i >> 5)), before = __ldg(packed + G + (i >> 5));
-    const unsigned bit = (unsigned)i & 31u;
-    plane[i] = ((m >> bit) & 1u) ? values[before + __popc(m & ((1u << bit) - 1u))] : 0.0f;
-  }
+  const uint32_t* aux = reinterpret_cast<const uint32_t*>(rec + 8 * n) + (int64_t)(2 * q) * G + (ii >> 5);
+  const uint32_t m = __ldg(aux), before = __ldg(aux + G);
+  const unsigned lane = (unsigned)ii & 31u;
+  float v = 0.0f;
+  if ((m >> lane) & 1u) v = ld_forcing(rec + q * n + before + __popc(m & ((1u << lane) - 1u)));
+  return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -150,7 +154,7 @@ __device__ __forceinline__ void budget_reduce(double* budget, double (*red)[NMP_
   }
 }
 
-template <class Opt, bool EXT, bool DIAG, bool BUDGET>
+template <class Opt, bool EXT, bool DIAG, bool BUDGET, bool PACKED = false>
 #ifndef NMP_MIN_BLOCKS
 #define NMP_MIN_BLOCKS 2
 #endif
@@ -228,14 +232,14 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
     Forcing f;
     if (a.records != nullptr) {   // records mode (uniform branch): interpolate + COSZ here, bit-identical to forcing_prep.cuh
       const StepForcing sf = a.tab[s];
-      const float* R = a.records + (int64_t)sf.rec0 * a.record_stride + ii;
+      const float* R = a.records + (int64_t)sf.rec0 * a.record_stride;
       float v[8];
       if (sf.w == 0.0f) {
-        static_for<0, 7>([&](auto q_) { constexpr int q = decltype(q_)::value; v[q] = ld_forcing(R + q * n); });
+        static_for<0, 7>([&](auto q_) { constexpr int q = decltype(q_)::value; v[q] = ld_record<PACKED>(R, q, sf.sp0, n, ii); });
       } else {
-        const float* R1 = a.records + (int64_t)sf.rec1 * a.record_stride + ii;
+        const float* R1 = a.records + (int64_t)sf.rec1 * a.record_stride;
         static_for<0, 7>([&](auto q_) { constexpr int q = decltype(q_)::value;
-          v[q] = lerp_rn(ld_forcing(R + q * n), ld_forcing(R1 + q * n), sf.w);
+          v[q] = lerp_rn(ld_record<PACKED>(R, q, sf.sp0, n, ii), ld_record<PACKED>(R1, q, sf.sp1, n, ii), sf.w);
         });
       }
       f.SFCTMP = v[F_SFCTMP]; f.SFCPRS = v[F_SFCPRS]; f.UU = v[F_UU]; f.VV = v[F_VV]; f.Q2 = v[F_Q2]; f.SOLDN = v[F_SOLDN];
@@ -247,8 +251,9 @@ __global__ void __maxnreg__(NMP_MAXNREG) column_step_kernel(const StepArgs a) {
 #ifdef NMP_PREFETCH_FORCING
       if (s + 1 < a.nsteps) {
         const float* Rn = a.records + (int64_t)a.tab[s + 1].rec0 * a.record_stride + ii;
+        const int spn = PACKED ? a.tab[s + 1].sp0 : 0;   // a packed plane's words are not at ii: not prefetched
         static_for<0, 7>([&](auto q_) { constexpr int q = decltype(q_)::value;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(Rn + q * n));
+          if (!((spn >> q) & 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(Rn + q * n));
         });
       }
 #endif

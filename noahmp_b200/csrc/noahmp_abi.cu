@@ -126,6 +126,7 @@ struct noahmp_ctx {
   cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // the copies out of a staging area have completed
   unsigned stage_next = 0;          // staging areas are used in turn
   std::vector<uint32_t> pack_scratch;   // the packer's intermediate copy of one plane's non-zero words
+  std::vector<int> slot_sparse;     // which planes of the record a ring slot holds are packed
   double pack_seconds = 0.0;        // wall time the calling thread has spent packing (its helpers work inside it)
   int64_t h2d_bytes = 0;            // bytes the advance_* entry points have copied host -> device
   int64_t launches = 0;
@@ -165,11 +166,13 @@ int cuda_fail(noahmp_ctx* c, cudaError_t e, const char* where) {
 
 typedef void (*StepKernel)(const StepArgs);
 
-StepKernel pick_kernel(bool is_default, bool diag, bool budget) {
+StepKernel pick_kernel(bool is_default, bool diag, bool budget, bool packed = false) {
 #ifdef NMP_EXPERIMENT_ONE_KERNEL   // tuning builds only (tools/tune_builds.sh): compile just the benchmarked variant
-  (void)is_default; (void)diag; (void)budget;
+  (void)is_default; (void)diag; (void)budget; (void)packed;
   return column_step_kernel<OptDefault, false, false, false>;
 #else
+  // zero-suppressed record planes: only noahmp_advance_records_host produces them, and it launches without diagnostics
+  if (packed) return is_default ? column_step_kernel<OptDefault, false, false, true, true> : column_step_kernel<OptRuntime, true, false, true, true>;
   if (is_default) {
     if (diag) return column_step_kernel<OptDefault, false, true, true>;
     if (budget) return column_step_kernel<OptDefault, false, false, true>;
@@ -442,6 +445,7 @@ int noahmp_set_tables(noahmp_ctx* c, const float* gen, int ngen, const float* so
 struct ForcingSource {
   const float* forcing = nullptr; int64_t forcing_stride = 0;
   const float* records = nullptr; int64_t record_stride = 0; const float* geo = nullptr; const noahmp_step_forcing* steps = nullptr;
+  const int* sp0 = nullptr; const int* sp1 = nullptr;   // per step: packed planes of rec0 / rec1 (null: dense records)
 };
 
 static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, int nsteps, float* state_dev,
@@ -471,11 +475,14 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
   a.static_i = static_i_dev; a.diag = diag_dev;
   a.records = src.records; a.record_stride = src.record_stride; a.geo = src.geo;
   std::memset(a.tab, 0, sizeof(a.tab));
+  bool packed = false;
   if (src.records)
     for (int s = 0; s < nsteps; ++s) {
       const noahmp_step_forcing& q = src.steps[s];
-      a.tab[s] = StepForcing{q.rec0, q.rec1, q.weight, q.sd, q.cd, q.ch0, q.sh0};
+      a.tab[s] = StepForcing{q.rec0, q.rec1, q.weight, q.sd, q.cd, q.ch0, q.sh0, src.sp0 ? src.sp0[s] : 0, src.sp1 ? src.sp1[s] : 0};
+      packed = packed || a.tab[s].sp0 != 0 || a.tab[s].sp1 != 0;
     }
+  if (packed && (diag_dev != nullptr || budget_dev == nullptr)) return fail(c, -1, "packed records are launched with a budget and without diagnostics");
   // every instantiation with diagnostics also sums the budget: a launch with diag_dev but without budget_dev folds into the scratch vector
   const bool sums = budget_dev != nullptr || diag_dev != nullptr;
   a.budget = sums ? c->dev_budget_rep : nullptr;
@@ -485,7 +492,7 @@ static int run_impl(noahmp_ctx* c, const noahmp_run_params* rp, int64_t ncol, in
   a.rc.zref = rp->zref; a.rc.co2_frac = rp->co2_frac; a.rc.o2_frac = rp->o2_frac; a.rc.foln = rp->foln;
   a.rc.yearlen = rp->yearlen; a.rc.julian0 = rp->julian0;
   a.opt = c->opt;
-  StepKernel k = pick_kernel(c->opt_is_default, diag_dev != nullptr, budget_dev != nullptr);
+  StepKernel k = pick_kernel(c->opt_is_default, diag_dev != nullptr, budget_dev != nullptr, packed);
   const int block = NMP_BLOCK;
   const int64_t grid = (ncol + block - 1) / block;
   if (grid > 0x7fffffffLL) return fail(c, -6, "ncol too large for one launch");
@@ -651,12 +658,7 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
   // k+1 run while launch k computes (a record shared by consecutive launches is copied once)
   const size_t n = (size_t)ncol, G = (n + 31) >> 5;
   const size_t host_rec_words = 8 * n;            // records_host is dense
-  // packing: candidate planes (noahmp_set_record_packing)
-  int cand[8], ncand = 0;
-  for (int q = 0; q < 8; ++q)
-    if ((c->pack_planes >> q) & 1u) cand[ncand++] = q;
-  const size_t stage_words = 2 * G + n;           // occupancy | before | values of one plane, as it crosses the link
-  const size_t rec_words = 8 * n + (size_t)ncand * stage_words;   // a ring slot: the eight planes + the landing areas of packed planes
+  const size_t rec_words = 8 * n + 16 * G;        // a ring slot: the eight planes + occupancy / before words of packed planes
   // Ring depth.  A launch needs at most 2 g records, so 4 g slots keep the copies one launch ahead.  A deeper ring lets them
   // run further ahead: the cost of a model step varies over the day (at night there is no radiation and no photosynthesis to
   // solve), so a run alternates between stretches bound by the link and stretches bound by the kernel, and only copies
@@ -702,7 +704,11 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
     c->cap_rring = need;
   }
   const int R = c->rring_slots;
-  // packing: the page-locked staging areas (kStageAreas, used in turn), the host threads
+  // packing: candidate planes, the page-locked staging areas (kStageAreas, used in turn), the host threads
+  int cand[8], ncand = 0;
+  for (int q = 0; q < 8; ++q)
+    if ((c->pack_planes >> q) & 1u) cand[ncand++] = q;
+  const size_t stage_words = 2 * G + n;           // occupancy | before | values of one plane
   if (ncand) {
     for (int k = 0; k < kStageAreas; ++k)
       if (!c->ev_stage[k]) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming));
@@ -727,7 +733,9 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
   // nothing of an earlier call may still read the ring when the first copy lands
   for (int k = 0; k < R; ++k) CUDA_TRY(c, cudaEventRecord(c->ev_slot[k], cs));
   std::vector<int> resident((size_t)R, -1);
+  c->slot_sparse.assign((size_t)R, 0);
   noahmp_step_forcing tab[MAX_RECORD_STEPS];
+  int sp0[MAX_RECORD_STEPS], sp1[MAX_RECORD_STEPS];
   for (int s0 = 0; s0 < nsteps; s0 += g) {
     const int nl = (nsteps - s0 < g) ? nsteps - s0 : g;
     bool copied = false;
@@ -762,17 +770,18 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
         }
         CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_slot[slot], 0));   // last launch that read this slot
         for (int qa = 0; qa < 8;) {
-          if ((sparse >> qa) & 1) {   // occupancy | before | non-zero words in one copy, expanded into the plane on the copy stream
+          if ((sparse >> qa) & 1) {
             int j = 0;
             while (cand[j] != qa) ++j;
             const uint32_t* st = c->stage + ((size_t)area * (size_t)ncand + (size_t)j) * stage_words;
-            uint32_t* land = reinterpret_cast<uint32_t*>(drec + 8 * n) + (size_t)j * stage_words;
-            const size_t words = 2 * G + (size_t)nnz[qa];
-            CUDA_TRY(c, cudaMemcpyAsync(land, st, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, c->copy_stream));
-            c->h2d_bytes += (int64_t)(sizeof(uint32_t) * words);
-            const int64_t blocks = (ncol + 255) / 256;
-            unpack_plane_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, c->copy_stream>>>(land, ncol, drec + (size_t)qa * n);
-            CUDA_TRY(c, cudaGetLastError());
+            CUDA_TRY(c, cudaMemcpyAsync(reinterpret_cast<uint32_t*>(drec + 8 * n) + (size_t)(2 * qa) * G, st, sizeof(uint32_t) * 2 * G,
+                                        cudaMemcpyHostToDevice, c->copy_stream));
+            c->h2d_bytes += (int64_t)(sizeof(uint32_t) * 2 * G);
+            if (nnz[qa] > 0) {
+              CUDA_TRY(c, cudaMemcpyAsync(drec + (size_t)qa * n, st + 2 * G, sizeof(float) * (size_t)nnz[qa], cudaMemcpyHostToDevice,
+                                          c->copy_stream));
+              c->h2d_bytes += (int64_t)(sizeof(float) * (size_t)nnz[qa]);
+            }
             ++qa;
           } else {   // a run of dense planes travels as one copy
             int qb = qa + 1;
@@ -785,11 +794,14 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
         }
         if (ncand) CUDA_TRY(c, cudaEventRecord(c->ev_stage[area], c->copy_stream));
         resident[(size_t)slot] = r;
+        c->slot_sparse[(size_t)slot] = sparse;
         copied = true;
       }
       tab[s] = q;
       tab[s].rec0 = need_rec[0] % R;
       tab[s].rec1 = need_rec[1] % R;
+      sp0[s] = c->slot_sparse[(size_t)tab[s].rec0];
+      sp1[s] = c->slot_sparse[(size_t)tab[s].rec1];
     }
     if (copied) {
       CUDA_TRY(c, cudaEventRecord(c->ev_rcopied, c->copy_stream));
@@ -799,6 +811,7 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
     r.julian0 = rp->julian0 + (double)s0 * (double)rp->dt / 86400.0;
     ForcingSource src;
     src.records = c->rring; src.record_stride = (int64_t)rec_words; src.geo = geo_dev; src.steps = tab;
+    src.sp0 = sp0; src.sp1 = sp1;
     const int rc = run_impl(c, &r, ncol, nl, state_dev, src, static_f_dev, static_i_dev, nullptr, c->dev_budget_scratch,
                             s0 + g >= nsteps ? 1 : 0);
     if (rc) return rc;

@@ -22,7 +22,7 @@ def numpy_pack(plane: np.ndarray):
 
 
 def numpy_unpack(occ, before, values, n):
-    """What the device does with a packed plane (csrc/column_step.cuh: unpack_plane_kernel), column by column."""
+    """What the step kernel's load does (csrc/column_step.cuh: ld_record), column by column."""
     i = np.arange(n)
     g, lane = i >> 5, (i & 31).astype(np.uint32)
     m = occ[g]
