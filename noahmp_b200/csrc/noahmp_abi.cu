@@ -752,7 +752,7 @@ int64_t noahmp_advance_records_host(noahmp_ctx* c, const noahmp_run_params* rp, 
         const float* hrec = records_host + (size_t)r * host_rec_words;
         float* drec = c->rring + (size_t)slot * rec_words;
         // pack the candidate planes of this record (host threads) while the device works on what is already queued;
-        // the staging area of the slot is free once the copies of the record it held before have completed
+        // a staging area is free once the copies of the record it held before have completed
         int sparse = 0;
         int64_t nnz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int area = (int)(c->stage_next % (unsigned)kStageAreas);   // copies leave in order: a few areas in turn suffice
